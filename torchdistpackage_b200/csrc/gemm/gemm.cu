@@ -1,0 +1,202 @@
+// Host side of the sm_100a tcgen05 GEMM: TMA tensor-map construction (cached), tile-shape
+// selection, persistent launch.  Kernel body: gemm_sm100.cuh.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+#include <unordered_map>
+
+#include "../common/tdp_api.h"
+#include "gemm_sm100.cuh"
+
+namespace tdp {
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld &&
+           box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h = h * 1315423911u + k.inner;
+    h = h * 1315423911u + k.outer;
+    h = h * 1315423911u + k.ld;
+    h = h * 1315423911u + k.box_inner * 1024 + k.box_outer;
+    return h;
+  }
+};
+
+// bf16 2-D row-major view [outer, inner] with leading dimension ld (elements), 128B swizzle.
+bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                  uint32_t box_inner, uint32_t box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{base, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return true;
+    }
+  }
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return true;
+}
+
+int g_num_sms = 0;
+
+template <int BLOCK_N>
+cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                        int grid, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_sm100_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotalBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err) {
+  static thread_local char msg[256];
+  *err = msg;
+  msg[0] = 0;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  if ((g.lda % 8) || (g.ldb % 8) || (reinterpret_cast<uintptr_t>(g.a) & 15) ||
+      (reinterpret_cast<uintptr_t>(g.b) & 15)) {
+    snprintf(msg, sizeof(msg), "gemm: operands must be 16-byte aligned with ld %% 8 == 0");
+    return -1;
+  }
+  if ((g.ldc % 8) || (g.N % 8)) {
+    snprintf(msg, sizeof(msg), "gemm: N and ldc must be multiples of 8 (N=%d ldc=%d)", g.N, g.ldc);
+    return -1;
+  }
+  const int sms = gemm_num_sms();
+  const int max_ctas = (g.max_ctas > 0 && g.max_ctas < sms) ? g.max_ctas : sms;
+  const int mb = (g.M + kBlockM - 1) / kBlockM;
+
+  int block_n = g.block_n;
+  if (block_n != 128 && block_n != 256) {
+    if (g.N <= 128) {
+      block_n = 128;
+    } else {
+      // pick the tile width with the smaller (waves x tile cost); ties -> 256 (less smem traffic)
+      const long t256 = static_cast<long>(mb) * ((g.N + 255) / 256);
+      const long t128 = static_cast<long>(mb) * ((g.N + 127) / 128);
+      const long c256 = ((t256 + max_ctas - 1) / max_ctas) * 256;
+      const long c128 = ((t128 + max_ctas - 1) / max_ctas) * 128;
+      block_n = (c128 < c256) ? 128 : 256;
+    }
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.num_m_blocks = mb;
+  p.num_n_blocks = (g.N + block_n - 1) / block_n;
+  p.num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  p.a_mn_major = g.trans_a ? 1 : 0;   // A stored [K, M]: M contiguous
+  p.b_mn_major = g.trans_b ? 0 : 1;   // B stored [K, N]: N contiguous
+  p.C = g.c; p.ldc = g.ldc; p.c_fp32 = g.c_fp32; p.accumulate = g.accumulate;
+  p.alpha = g.alpha;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(g.bias);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(g.residual);
+  p.ld_res = g.ld_res;
+  p.aux_in = reinterpret_cast<const __nv_bfloat16*>(g.aux_in);
+  p.aux_out = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
+  p.ld_aux = g.ld_aux;
+  p.act = g.act;
+  p.group_m = 8;
+  p.comm_mode = g.comm_mode;
+  p.rank = g.rank; p.world = g.world;
+  p.rows_per_chunk = g.rows_per_chunk;
+  p.chunk_flags = g.chunk_flags;
+  p.flag_target = g.flag_target;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    p.peer_out[i] = g.peer_out[i];
+    p.peer_tile_counter[i] = g.peer_tile_counter[i];
+  }
+  if (p.comm_mode != COMM_NONE) {
+    if (g.world < 1 || g.world > kMaxPeers || g.rows_per_chunk % kBlockM != 0 ||
+        g.rows_per_chunk * g.world != g.M) {
+      snprintf(msg, sizeof(msg), "gemm(comm): M=%d must equal world(%d) x rows_per_chunk(%d), "
+               "rows_per_chunk %% 128 == 0", g.M, g.world, g.rows_per_chunk);
+      return -1;
+    }
+    // chunk-major tile order: a raster group never straddles two chunks
+    const int bpc = g.rows_per_chunk / kBlockM;
+    int gm = 8;
+    while (bpc % gm) gm >>= 1;
+    p.group_m = gm;
+  }
+
+  CUtensorMap ta, tb;
+  bool ok;
+  if (!g.trans_a) ok = make_tmap_2d(&ta, g.a, g.K, g.M, g.lda, kBlockK, kBlockM);
+  else            ok = make_tmap_2d(&ta, g.a, g.M, g.K, g.lda, 64, kBlockK);
+  if (!ok) { snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(A) failed"); return -2; }
+  if (g.trans_b)  ok = make_tmap_2d(&tb, g.b, g.K, g.N, g.ldb, kBlockK, block_n);
+  else            ok = make_tmap_2d(&tb, g.b, g.N, g.K, g.ldb, 64, kBlockK);
+  if (!ok) { snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(B) failed"); return -2; }
+
+  const long tiles = static_cast<long>(p.num_m_blocks) * p.num_n_blocks;
+  const int grid = static_cast<int>(tiles < max_ctas ? tiles : max_ctas);
+  cudaError_t e = (block_n == 256) ? launch_impl<256>(ta, tb, p, grid, stream)
+                                   : launch_impl<128>(ta, tb, p, grid, stream);
+  if (e != cudaSuccess) {
+    snprintf(msg, sizeof(msg), "gemm launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace tdp

@@ -1,0 +1,415 @@
+// Warp-specialised persistent bf16 GEMM for sm_100a:
+//   TMA (128B swizzle) -> smem ring -> tcgen05.mma (single elected thread, cta_group::1, M=128)
+//   -> fp32 accumulators in TMEM (double buffered) -> tcgen05.ld epilogue with fused
+//   bias / GELU / dGELU / residual / accumulate / peer-scatter.
+//
+// This header is the shared main loop.  Plain GEMM (gemm.cu) and the GEMM+collective kernels
+// (gemm_comm.cu: all-gather->GEMM, GEMM->reduce-scatter, GEMM->all-reduce) instantiate it with
+// different tile-order / producer-wait / epilogue-destination policies selected at run time
+// through GemmParams (all branches are warp uniform).
+//
+// Replaces the reference's torch.matmul(x, W) + in-place bias (tensor_parallel/tp_utils.py:170-174)
+// and, in the fused variants, the collective that follows/precedes it (tp_utils.py:44,67,84).
+#pragma once
+#include "../common/ptx.cuh"
+
+namespace tdp {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;     // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumEpilogueWarps = 4;
+constexpr int kGemmThreads = 32 * (2 + kNumEpilogueWarps);  // warp0 TMA, warp1 MMA, warps2-5 epi
+constexpr int kMaxPeers = 8;
+
+enum GemmAct : int {
+  ACT_NONE = 0,
+  ACT_GELU_TANH = 1,
+  ACT_GELU_ERF = 2,
+  ACT_DGELU_TANH = 3,  // out = acc * gelu'(aux_in)
+  ACT_DGELU_ERF = 4,
+};
+
+enum GemmCommMode : int {
+  COMM_NONE = 0,
+  // A operand rows arrive chunk by chunk (all-gather): the TMA producer waits on
+  // chunk_flags[chunk] >= flag_target before loading A rows of that chunk.
+  COMM_AG_WAIT_A = 1,
+  // C rows are partial sums destined for the rank that owns the row chunk: the epilogue stores
+  // the tile into that rank's staging buffer (peer memory) and bumps its per-chunk counter.
+  COMM_RS_SCATTER = 2,
+};
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int a_mn_major, b_mn_major;
+  // epilogue
+  void* C;          // bf16 or fp32 [M, ldc]
+  int ldc;
+  int c_fp32;
+  int accumulate;   // C += result (fp32 or bf16 read-modify-write)
+  float alpha;
+  const __nv_bfloat16* bias;      // [N] or null
+  const __nv_bfloat16* residual;  // [M, ld_res] or null
+  int ld_res;
+  const __nv_bfloat16* aux_in;    // [M, ld_aux] pre-activation for dGELU
+  __nv_bfloat16* aux_out;         // [M, ld_aux] pre-activation copy (value before activation)
+  int ld_aux;
+  int act;
+  int group_m;                    // rasterisation group
+  // ---- fused collective hooks ----
+  int comm_mode;
+  int rank, world;
+  int rows_per_chunk;             // M / world (chunk c belongs to rank c)
+  uint32_t* chunk_flags;          // [world] local flags (AG wait) -- device memory of this rank
+  uint32_t flag_target;           // monotonically increasing epoch value
+  // RS scatter: peer_out[r] = base of rank r's staging buffer [world][rows_per_chunk][ldc] bf16
+  void* peer_out[kMaxPeers];
+  uint32_t* peer_tile_counter[kMaxPeers];  // per-rank counter array [world(src)] bumped per tile
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+  static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+};
+
+// tile index -> (m_block, n_block) with grouped rasterisation so that concurrently running CTAs
+// share B tiles (and a few A tiles) in L2.  `m_shift` rotates the m order (used by the fused
+// collectives so that every rank starts on a different chunk).
+TDP_DEVICE void tile_to_mn(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+  const int group = p.group_m;
+  const int tiles_per_group = group * p.num_n_blocks;
+  const int g = tile / tiles_per_group;
+  const int first_m = g * group;
+  const int rows_in_group = min(group, p.num_m_blocks - first_m);
+  const int in_group = tile - g * tiles_per_group;
+  m_blk = first_m + in_group % rows_in_group;
+  n_blk = in_group / rows_in_group;
+}
+
+// For the collective variants tiles are ordered chunk-major: chunk order starts at a rank
+// dependent offset.  AG: local chunk first, then rank+1, ... (data arrives in that order).
+// RS: remote chunks first (rank+1 ...), local chunk last (it needs no transfer).
+TDP_DEVICE int remap_m_block(const GemmParams& p, int m_blk) {
+  if (p.comm_mode == COMM_NONE) return m_blk;
+  const int blocks_per_chunk = p.rows_per_chunk / kBlockM;
+  const int c = m_blk / blocks_per_chunk;
+  const int r = m_blk - c * blocks_per_chunk;
+  const int shift = (p.comm_mode == COMM_AG_WAIT_A) ? p.rank : (p.rank + 1);
+  int chunk = c + shift;
+  chunk = chunk >= p.world ? chunk - p.world : chunk;
+  return chunk * blocks_per_chunk + r;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (<= 512)
+  static_assert(kTmemCols <= 512, "TMEM overflow");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp_idx == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kNumEpilogueWarps);
+    }
+    fence_barrier_init();
+  } else if (warp_idx == 1) {
+    tmem_alloc<kTmemCols>(tmem_holder);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp_idx == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_to_mn(p, tile, m_blk, n_blk);
+        m_blk = remap_m_block(p, m_blk);
+        if (p.comm_mode == COMM_AG_WAIT_A) {
+          const int chunk = (m_blk * kBlockM) / p.rows_per_chunk;
+          if (chunk != p.rank) {
+            while (ld_acquire_sys(p.chunk_flags + chunk) < p.flag_target) {
+            }
+            // peer / comm-CTA writes (generic proxy) -> our TMA reads (async proxy)
+            fence_proxy_async_all();
+          }
+        }
+        const int m0 = m_blk * kBlockM;
+        const int n0 = n_blk * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          uint8_t* sa = smem_a + stage * S::kStageBytesA;
+          uint8_t* sb = smem_b + stage * S::kStageBytesB;
+          const int k0 = kb * kBlockK;
+          if (!p.a_mn_major) {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (64 * kBlockK * 2), m0 + 64 * j, k0);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (64 * kBlockK * 2), n0 + 64 * j, k0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = make_idesc_bf16_f32(kBlockM, BLOCK_N, p.a_mn_major, p.b_mn_major);
+    // descriptor geometry (bytes)
+    const uint32_t a_lbo = p.a_mn_major ? 64 * kBlockK * 2 : 0;
+    const uint32_t b_lbo = p.b_mn_major ? 64 * kBlockK * 2 : 0;
+    const uint32_t a_kstep = p.a_mn_major ? kUmmaK * 128 : kUmmaK * 2;
+    const uint32_t b_kstep = p.b_mn_major ? kUmmaK * 128 : kUmmaK * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // wait until the epilogue has drained this accumulator stage
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem_a + stage * S::kStageBytesA);
+          const uint32_t sb = smem_u32(smem_b + stage * S::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // frees the smem slot when MMAs finish
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    // A warp may only touch TMEM lanes [32*(warp_idx%4), +32).
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_to_mn(p, tile, m_blk, n_blk);
+      m_blk = remap_m_block(p, m_blk);
+      const int row = m_blk * kBlockM + quad * 32 + lane;
+      const int n0 = n_blk * BLOCK_N;
+      const bool row_ok = row < p.M;
+
+      // destination (plain: C ; RS scatter: owner's staging slot for our rank)
+      uint8_t* c_row;
+      int dst_rank = -1;
+      if (p.comm_mode == COMM_RS_SCATTER) {
+        dst_rank = (m_blk * kBlockM) / p.rows_per_chunk;
+        const int local_row = row - dst_rank * p.rows_per_chunk;
+        c_row = reinterpret_cast<uint8_t*>(p.peer_out[dst_rank]) +
+                (static_cast<size_t>(p.rank) * p.rows_per_chunk + local_row) *
+                    static_cast<size_t>(p.ldc) * 2;
+      } else {
+        c_row = reinterpret_cast<uint8_t*>(p.C) +
+                static_cast<size_t>(row) * p.ldc * (p.c_fp32 ? 4 : 2);
+      }
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          const bool full = (col0 + 32 <= p.N);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || col0 + j + 8 <= p.N) {
+                const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
+                const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y),
+                             b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
+                v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b1.x; v[j + 3] += b1.y;
+                v[j + 4] += b2.x; v[j + 5] += b2.y; v[j + 6] += b3.x; v[j + 7] += b3.y;
+              }
+            }
+          }
+          if (p.aux_out != nullptr) {
+            __nv_bfloat16* arow = p.aux_out + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || col0 + j + 8 <= p.N) {
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(arow + j) = o;
+              }
+            }
+          }
+          if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+          } else if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == ACT_DGELU_TANH || p.act == ACT_DGELU_ERF) {
+            const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || col0 + j + 8 <= p.N) {
+                const uint4 z = *reinterpret_cast<const uint4*>(zrow + j);
+                float zz[8];
+                float2 t;
+                t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
+                t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
+                t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
+                t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  v[j + q] *= (p.act == ACT_DGELU_TANH) ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+            const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row) * p.ld_res + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || col0 + j + 8 <= p.N) {
+                const uint4 z = *reinterpret_cast<const uint4*>(rrow + j);
+                float2 t;
+                t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
+                t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
+                t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
+                t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
+              }
+            }
+          }
+          if (p.c_fp32) {
+            float* crow = reinterpret_cast<float*>(c_row) + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full || col0 + j + 4 <= p.N) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(crow + j);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(crow + j) = o;
+              }
+            }
+          } else {
+            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(c_row) + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || col0 + j + 8 <= p.N) {
+                if (p.accumulate) {
+                  const uint4 z = *reinterpret_cast<const uint4*>(crow + j);
+                  float2 t;
+                  t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
+                  t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
+                  t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
+                  t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
+                }
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                if (p.comm_mode == COMM_RS_SCATTER) st_na_v4(crow + j, o);   // peer store
+                else *reinterpret_cast<uint4*>(crow + j) = o;
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+
+      if (p.comm_mode == COMM_RS_SCATTER) {
+        // publish this warp's quarter of the tile to the owner: all lanes' peer stores must be
+        // ordered before the counter bump (release at system scope).
+        __syncwarp();
+        if (lane == 0) {
+          fence_acq_rel_sys();
+          red_add_release_sys(p.peer_tile_counter[dst_rank] + p.rank, 1u);
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace tdp
