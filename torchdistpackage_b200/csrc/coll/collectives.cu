@@ -1,0 +1,530 @@
+// NVSwitch collectives over symmetric memory, written for 8xB200 (NVLink 5, NVLS multicast).
+//
+//   * all_reduce      two-shot: every rank reduces 1/N of the buffer -- in the switch with
+//                     multimem.ld_reduce (NVLS) or by reading its slice from every peer (P2P) --
+//                     and broadcasts the result with multimem.st / peer stores.
+//   * reduce_scatter  first half of the above, result written to a local (bf16|fp32) tensor with an
+//                     optional fp32 accumulate (ZeRO master-grad epilogue).
+//   * all_gather      multimem.st (one store fans out in the switch) or peer stores of my slice.
+//   * rs_reduce       second stage of the fused GEMM->reduce-scatter / GEMM->all-reduce: waits for
+//                     the per-source tile counters bumped by the GEMM epilogues, sums the partials.
+//   * a2a rows        MoE dispatch / combine: row-granular peer stores / loads.
+//
+// Cross-GPU synchronisation uses flag words in the symmetric signal pad: release/acquire CAS at
+// system scope, one slot per (block, peer) so blocks synchronise independently (no grid sync).
+//
+// These replace the reference's NCCL calls: dist.all_reduce on DDP buckets (ddp/naive_ddp.py:104-127),
+// ZeRO's all_reduce + per-tensor broadcast (ddp/zero_optim.py:73-95,282-287), TP/SP collectives
+// (parallel/tensor_parallel/tp_utils.py:44,67,84).
+#include "../common/ptx.cuh"
+#include "../common/tdp_api.h"
+
+namespace tdp {
+
+namespace {
+
+constexpr int kCollThreads = 512;
+constexpr int kMaxCollBlocks = 64;          // barrier slots reserved per signal pad region
+constexpr int kBarrierSlotWords = kMaxCollBlocks * kApiMaxPeers;   // words per barrier "slot"
+
+struct PeerPtrs {
+  void* buf[kApiMaxPeers];
+  uint32_t* signal[kApiMaxPeers];
+};
+
+__device__ __forceinline__ void put_signal(uint32_t* addr) {
+  uint32_t old;
+  do {
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+  } while (old != 0u);
+}
+__device__ __forceinline__ void wait_signal(uint32_t* addr) {
+  uint32_t old;
+  do {
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+  } while (old != 1u);
+}
+
+// Block-level barrier with the same-index block of every peer.  Slot layout (uint32 words):
+//   pad[slot_base + blockIdx.x * world + src_rank]
+__device__ __forceinline__ void block_barrier(const PeerPtrs& pp, int rank, int world,
+                                              int slot_base) {
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int peer = threadIdx.x;
+    put_signal(pp.signal[peer] + slot_base + blockIdx.x * world + rank);
+    wait_signal(pp.signal[rank] + slot_base + blockIdx.x * world + peer);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint4 scale_bf16x8(uint4 v, float s) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z),
+         d = unpack_bf16x2(v.w);
+  v.x = pack_bf16x2(a.x * s, a.y * s);
+  v.y = pack_bf16x2(b.x * s, b.y * s);
+  v.z = pack_bf16x2(c.x * s, c.y * s);
+  v.w = pack_bf16x2(d.x * s, d.y * s);
+  return v;
+}
+__device__ __forceinline__ void acc_bf16x8(float (&acc)[8], uint4 v) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z),
+         d = unpack_bf16x2(v.w);
+  acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+  acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8], float s) {
+  uint4 v;
+  v.x = pack_bf16x2(acc[0] * s, acc[1] * s);
+  v.y = pack_bf16x2(acc[2] * s, acc[3] * s);
+  v.z = pack_bf16x2(acc[4] * s, acc[5] * s);
+  v.w = pack_bf16x2(acc[6] * s, acc[7] * s);
+  return v;
+}
+
+// reduce 16 bytes at byte offset `off` across all ranks. kMc: in-switch, else peer loads (fixed
+// rank order starting at rank 0 -> bitwise identical result on every rank).
+template <bool kMc, bool kFp32>
+__device__ __forceinline__ uint4 reduce16(const PeerPtrs& pp, const char* mc, int world,
+                                          size_t off, float scale) {
+  if constexpr (kMc) {
+    if constexpr (kFp32) {
+      float4 f = multimem_ld_reduce_f32x4(mc + off);
+      f.x *= scale; f.y *= scale; f.z *= scale; f.w *= scale;
+      return *reinterpret_cast<uint4*>(&f);
+    } else {
+      uint4 v = multimem_ld_reduce_bf16x8(mc + off);
+      return scale == 1.f ? v : scale_bf16x8(v, scale);
+    }
+  } else {
+    if constexpr (kFp32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p) {
+        if (p < world) {
+          uint4 u = ld_nc_v4(reinterpret_cast<const char*>(pp.buf[p]) + off);
+          float4 f = *reinterpret_cast<float4*>(&u);
+          acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+        }
+      }
+      acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+      return *reinterpret_cast<uint4*>(&acc);
+    } else {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      uint4 vals[kApiMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p)
+        if (p < world) vals[p] = ld_nc_v4(reinterpret_cast<const char*>(pp.buf[p]) + off);
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p)
+        if (p < world) acc_bf16x8(acc, vals[p]);
+      return pack8(acc, scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// all-reduce (two-shot, in place)
+// ------------------------------------------------------------------------------------------
+template <bool kMc, bool kFp32>
+__global__ void __launch_bounds__(kCollThreads)
+all_reduce_two_shot_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset,
+                           size_t n_vec /*16-byte vectors*/, float scale, int slot_base) {
+  block_barrier(pp, rank, world, slot_base);
+  // my part: vectors [lo, hi)
+  const size_t per = (n_vec + world - 1) / world;
+  const size_t lo = min(per * rank, n_vec), hi = min(lo + per, n_vec);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = lo + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hi;
+       i += stride) {
+    const size_t off = offset + i * 16;
+    const uint4 v = reduce16<kMc, kFp32>(pp, mc, world, off, scale);
+    if constexpr (kMc) {
+      multimem_st_v4(mc + off, v);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p)
+        if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + off, v);
+    }
+  }
+  block_barrier(pp, rank, world, slot_base + kBarrierSlotWords);
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce-scatter: slice `rank` of [world x slice] -> out (local)
+// ------------------------------------------------------------------------------------------
+template <bool kMc, bool kFp32In>
+__global__ void __launch_bounds__(kCollThreads)
+reduce_scatter_kernel(const __grid_constant__ PeerPtrs pp, const char* mc, int rank, int world, size_t offset,
+                      size_t slice_vec, float scale, void* out, int out_fp32, int accumulate,
+                      int slot_base) {
+  block_barrier(pp, rank, world, slot_base);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t base = offset + static_cast<size_t>(rank) * slice_vec * 16;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slice_vec;
+       i += stride) {
+    const uint4 v = reduce16<kMc, kFp32In>(pp, mc, world, base + i * 16, scale);
+    if constexpr (kFp32In) {
+      float4 f = *reinterpret_cast<const float4*>(&v);
+      float4* o = reinterpret_cast<float4*>(out) + i;
+      if (accumulate) { float4 t = *o; f.x += t.x; f.y += t.y; f.z += t.z; f.w += t.w; }
+      *o = f;
+    } else if (out_fp32) {
+      float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z),
+             d = unpack_bf16x2(v.w);
+      float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+      float4 f0 = make_float4(a.x, a.y, b.x, b.y), f1 = make_float4(c.x, c.y, d.x, d.y);
+      if (accumulate) {
+        float4 t0 = o[0], t1 = o[1];
+        f0.x += t0.x; f0.y += t0.y; f0.z += t0.z; f0.w += t0.w;
+        f1.x += t1.x; f1.y += t1.y; f1.z += t1.z; f1.w += t1.w;
+      }
+      o[0] = f0; o[1] = f1;
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(out) + i;
+      if (accumulate) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        acc_bf16x8(acc, v); acc_bf16x8(acc, *o);
+        *o = pack8(acc, 1.f);
+      } else {
+        *o = v;
+      }
+    }
+  }
+  block_barrier(pp, rank, world, slot_base + kBarrierSlotWords);
+}
+
+// ------------------------------------------------------------------------------------------
+// all-gather: my slice (local src) -> slot `rank` of the symmetric region on every rank
+// ------------------------------------------------------------------------------------------
+template <bool kMc>
+__global__ void __launch_bounds__(kCollThreads)
+all_gather_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset, size_t slice_vec,
+                  const uint4* src, int slot_base, uint32_t* flag_base_unused) {
+  block_barrier(pp, rank, world, slot_base);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t base = offset + static_cast<size_t>(rank) * slice_vec * 16;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slice_vec;
+       i += stride) {
+    const uint4 v = src ? src[i]
+                        : *reinterpret_cast<const uint4*>(
+                              reinterpret_cast<const char*>(pp.buf[rank]) + base + i * 16);
+    if constexpr (kMc) {
+      multimem_st_v4(mc + base + i * 16, v);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p)
+        if (p < world && (p != rank || src != nullptr))
+          st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + base + i * 16, v);
+    }
+  }
+  block_barrier(pp, rank, world, slot_base + kBarrierSlotWords);
+}
+
+// all-gather that publishes a per-source-chunk flag instead of a trailing barrier: consumers
+// (the fused all-gather->GEMM producer warp) poll flag[src] >= value on their own pad.
+// One counter per source rank is bumped once per *block*; consumer target = value * gridDim.x
+// is avoided by letting only the last block to finish (device-wide ticket) publish.
+template <bool kMc>
+__global__ void __launch_bounds__(kCollThreads)
+all_gather_signal_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset,
+                         size_t slice_vec, const uint4* src, size_t flag_word, uint32_t flag_value,
+                         uint32_t* ticket) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t base = offset + static_cast<size_t>(rank) * slice_vec * 16;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slice_vec;
+       i += stride) {
+    const uint4 v = src[i];
+    if constexpr (kMc) {
+      multimem_st_v4(mc + base + i * 16, v);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kApiMaxPeers; ++p)
+        if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + base + i * 16, v);
+    }
+  }
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    fence_acq_rel_sys();
+    const uint32_t t = atomicAdd(ticket, 1u);
+    fence_acq_rel_sys();   // acquire side: order the other blocks' stores before the flag publish
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    // every block's stores are ordered before its ticket increment (fence + atomic); the last
+    // block observes all tickets, so a system-scope release store now publishes the whole slice.
+    if (threadIdx.x < world) {
+      fence_acq_rel_sys();
+      st_release_sys(pp.signal[threadIdx.x] + flag_word + rank, flag_value);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// second stage of fused GEMM->reduce-scatter / GEMM->all-reduce
+// ------------------------------------------------------------------------------------------
+template <bool kMc>
+__global__ void __launch_bounds__(kCollThreads)
+rs_reduce_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, RsReduceLaunch r) {
+  // wait until every source rank has delivered all of its tiles for my chunk
+  if (threadIdx.x < world) {
+    const uint32_t* cnt = pp.signal[rank] + r.counter_word_offset + threadIdx.x;
+    while (static_cast<int32_t>(ld_acquire_sys(cnt) - r.counter_target) < 0) {
+    }
+  }
+  __syncthreads();
+  const int vec_per_row = r.cols / 8;
+  const size_t total = static_cast<size_t>(r.rows) * vec_per_row;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const char* stage = reinterpret_cast<const char*>(pp.buf[rank]) + r.offset;
+  const size_t slice_bytes = static_cast<size_t>(r.rows) * r.ld * 2;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += stride) {
+    const int row = static_cast<int>(i / vec_per_row);
+    const int col = static_cast<int>(i - static_cast<size_t>(row) * vec_per_row) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint4 vals[kApiMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kApiMaxPeers; ++p)
+      if (p < world)
+        vals[p] = ld_volatile_v4(stage + p * slice_bytes +
+                                 (static_cast<size_t>(row) * r.ld + col) * 2);
+#pragma unroll
+    for (int p = 0; p < kApiMaxPeers; ++p)
+      if (p < world) acc_bf16x8(acc, vals[p]);
+    if (r.bias) {
+      acc_bf16x8(acc, *reinterpret_cast<const uint4*>(
+                          reinterpret_cast<const __nv_bfloat16*>(r.bias) + col));
+    }
+    if (r.residual) {
+      acc_bf16x8(acc, *reinterpret_cast<const uint4*>(
+                          reinterpret_cast<const __nv_bfloat16*>(r.residual) +
+                          static_cast<size_t>(row) * r.ld_res + col));
+    }
+    const uint4 o = pack8(acc, 1.f);
+    if (!r.broadcast) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(r.out) +
+                                static_cast<size_t>(row) * r.ld_out + col) = o;
+    } else {
+      const size_t off = r.bcast_offset +
+                         ((static_cast<size_t>(rank) * r.rows + row) * r.ld_out + col) * 2;
+      if constexpr (kMc) {
+        multimem_st_v4(mc + off, o);
+      } else {
+#pragma unroll
+        for (int p = 0; p < kApiMaxPeers; ++p)
+          if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + off, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MoE all-to-all (row granular)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+a2a_scatter_rows_kernel(const __grid_constant__ PeerPtrs pp, size_t offset, const uint4* src, int n_rows, int vec_per_row,
+                        const int* dst_rank, const int* dst_row) {
+  const int warps_per_block = blockDim.x / 32;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + threadIdx.x / 32; row < n_rows;
+       row += gridDim.x * warps_per_block) {
+    const int dr = dst_row[row];
+    if (dr < 0) continue;
+    char* dst = reinterpret_cast<char*>(pp.buf[dst_rank[row]]) + offset +
+                static_cast<size_t>(dr) * vec_per_row * 16;
+    const uint4* s = src + static_cast<size_t>(row) * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) st_na_v4(dst + v * 16, s[v]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+a2a_gather_rows_kernel(const __grid_constant__ PeerPtrs pp, size_t offset, uint4* out, int n_rows, int vec_per_row,
+                       const int* src_rank, const int* src_row, const float* scale,
+                       int accumulate) {
+  const int warps_per_block = blockDim.x / 32;
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * warps_per_block + threadIdx.x / 32; row < n_rows;
+       row += gridDim.x * warps_per_block) {
+    const int sr = src_row[row];
+    uint4* o = out + static_cast<size_t>(row) * vec_per_row;
+    if (sr < 0) {
+      if (!accumulate)
+        for (int v = lane; v < vec_per_row; v += 32) o[v] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const char* s = reinterpret_cast<const char*>(pp.buf[src_rank[row]]) + offset +
+                    static_cast<size_t>(sr) * vec_per_row * 16;
+    const float w = scale ? scale[row] : 1.f;
+    for (int v = lane; v < vec_per_row; v += 32) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      acc_bf16x8(acc, ld_nc_v4(s + v * 16));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] *= w;
+      if (accumulate) acc_bf16x8(acc, o[v]);
+      o[v] = pack8(acc, 1.f);
+    }
+  }
+}
+
+__global__ void barrier_only_kernel(const __grid_constant__ PeerPtrs pp, int rank, int world, int slot_base) {
+  block_barrier(pp, rank, world, slot_base);
+}
+
+PeerPtrs to_pp(const SymmPeers& s) {
+  PeerPtrs p;
+  for (int i = 0; i < kApiMaxPeers; ++i) {
+    p.buf[i] = s.buf[i];
+    p.signal[i] = s.signal[i];
+  }
+  return p;
+}
+
+int pick_blocks(size_t n_vec_per_rank, int max_ctas) {
+  size_t want = (n_vec_per_rank + kCollThreads * 4 - 1) / (kCollThreads * 4);
+  int cap = max_ctas > 0 ? max_ctas : 32;
+  if (cap > kMaxCollBlocks) cap = kMaxCollBlocks;
+  if (want < 1) want = 1;
+  return static_cast<int>(want < static_cast<size_t>(cap) ? want : cap);
+}
+
+uint32_t* g_ticket = nullptr;
+uint32_t* ticket_counter() {
+  if (!g_ticket) {
+    cudaMalloc(&g_ticket, 64 * sizeof(uint32_t));
+    cudaMemset(g_ticket, 0, 64 * sizeof(uint32_t));
+  }
+  return g_ticket;
+}
+
+}  // namespace
+
+// Signal pad word layout (per symmetric allocation):
+//   [0, 2*kBarrierSlotWords)                       barrier slots of collective kernels (A/B)
+//   [2*kBarrierSlotWords, 3*kBarrierSlotWords)     standalone barrier
+//   [kUserWordBase, ...)                            chunk flags / tile counters (fused GEMM paths)
+constexpr int kStandaloneBarrierBase = 2 * kBarrierSlotWords;
+
+void launch_symm_barrier(const SymmPeers& s, int slot, cudaStream_t stream) {
+  barrier_only_kernel<<<1, 32, 0, stream>>>(to_pp(s), s.rank, s.world,
+                                            kStandaloneBarrierBase + slot * kApiMaxPeers);
+}
+
+void launch_all_reduce(const SymmPeers& s, size_t offset, size_t numel, int dtype, float scale,
+                       int algo, int max_ctas, cudaStream_t stream) {
+  const size_t elem = dtype == 1 ? 4 : 2;
+  const size_t n_vec = numel * elem / 16;
+  const bool mc = (algo == 3) || (algo == 0 && s.mc_buf != nullptr);
+  const int blocks = pick_blocks(n_vec / (s.world > 0 ? s.world : 1), max_ctas);
+  PeerPtrs pp = to_pp(s);
+  char* mcp = reinterpret_cast<char*>(s.mc_buf);
+  if (mc) {
+    if (dtype == 1)
+      all_reduce_two_shot_kernel<true, true><<<blocks, kCollThreads, 0, stream>>>(
+          pp, mcp, s.rank, s.world, offset, n_vec, scale, 0);
+    else
+      all_reduce_two_shot_kernel<true, false><<<blocks, kCollThreads, 0, stream>>>(
+          pp, mcp, s.rank, s.world, offset, n_vec, scale, 0);
+  } else {
+    if (dtype == 1)
+      all_reduce_two_shot_kernel<false, true><<<blocks, kCollThreads, 0, stream>>>(
+          pp, mcp, s.rank, s.world, offset, n_vec, scale, 0);
+    else
+      all_reduce_two_shot_kernel<false, false><<<blocks, kCollThreads, 0, stream>>>(
+          pp, mcp, s.rank, s.world, offset, n_vec, scale, 0);
+  }
+}
+
+void launch_reduce_scatter(const SymmPeers& s, size_t offset, size_t slice_numel, int dtype,
+                           float scale, void* out, int out_fp32, int accumulate_out, int use_mc,
+                           int max_ctas, cudaStream_t stream) {
+  const size_t elem = dtype == 1 ? 4 : 2;
+  const size_t slice_vec = slice_numel * elem / 16;
+  const bool mc = use_mc && s.mc_buf != nullptr;
+  const int blocks = pick_blocks(slice_vec, max_ctas);
+  PeerPtrs pp = to_pp(s);
+  const char* mcp = reinterpret_cast<const char*>(s.mc_buf);
+#define TDP_RS(MC, F32)                                                                      \
+  reduce_scatter_kernel<MC, F32><<<blocks, kCollThreads, 0, stream>>>(                        \
+      pp, mcp, s.rank, s.world, offset, slice_vec, scale, out, out_fp32, accumulate_out, 0)
+  if (mc) { if (dtype == 1) TDP_RS(true, true); else TDP_RS(true, false); }
+  else    { if (dtype == 1) TDP_RS(false, true); else TDP_RS(false, false); }
+#undef TDP_RS
+}
+
+void launch_all_gather(const SymmPeers& s, size_t offset, size_t slice_numel, int elem_bytes,
+                       const void* src, int use_mc, int max_ctas, cudaStream_t stream) {
+  const size_t slice_vec = slice_numel * elem_bytes / 16;
+  const bool mc = use_mc && s.mc_buf != nullptr;
+  const int blocks = pick_blocks(slice_vec, max_ctas);
+  PeerPtrs pp = to_pp(s);
+  char* mcp = reinterpret_cast<char*>(s.mc_buf);
+  if (mc)
+    all_gather_kernel<true><<<blocks, kCollThreads, 0, stream>>>(
+        pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src), 0,
+        nullptr);
+  else
+    all_gather_kernel<false><<<blocks, kCollThreads, 0, stream>>>(
+        pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src), 0,
+        nullptr);
+}
+
+void launch_all_gather_signal(const SymmPeers& s, size_t offset, size_t slice_bytes,
+                              const void* src, size_t flag_word_offset, uint32_t flag_value,
+                              int use_mc, int max_ctas, cudaStream_t stream) {
+  const size_t slice_vec = slice_bytes / 16;
+  const bool mc = use_mc && s.mc_buf != nullptr;
+  const int blocks = pick_blocks(slice_vec, max_ctas);
+  PeerPtrs pp = to_pp(s);
+  char* mcp = reinterpret_cast<char*>(s.mc_buf);
+  uint32_t* ticket = ticket_counter();
+  if (mc)
+    all_gather_signal_kernel<true><<<blocks, kCollThreads, 0, stream>>>(
+        pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src),
+        flag_word_offset, flag_value, ticket);
+  else
+    all_gather_signal_kernel<false><<<blocks, kCollThreads, 0, stream>>>(
+        pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src),
+        flag_word_offset, flag_value, ticket);
+}
+
+void launch_rs_reduce(const SymmPeers& s, const RsReduceLaunch& r, int use_mc, int max_ctas,
+                      cudaStream_t stream) {
+  const bool mc = use_mc && s.mc_buf != nullptr;
+  const size_t total_vec = static_cast<size_t>(r.rows) * (r.cols / 8);
+  int blocks = pick_blocks(total_vec, max_ctas > 0 ? max_ctas : 64);
+  PeerPtrs pp = to_pp(s);
+  char* mcp = reinterpret_cast<char*>(s.mc_buf);
+  if (mc) rs_reduce_kernel<true><<<blocks, kCollThreads, 0, stream>>>(pp, mcp, s.rank, s.world, r);
+  else    rs_reduce_kernel<false><<<blocks, kCollThreads, 0, stream>>>(pp, mcp, s.rank, s.world, r);
+}
+
+void launch_a2a_scatter_rows(const SymmPeers& s, size_t offset, const void* src, int n_rows,
+                             int hidden, const int* dst_rank, const int* dst_row,
+                             cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  const int vec_per_row = hidden * 2 / 16;
+  int blocks = (n_rows + 7) / 8;
+  if (blocks > 296) blocks = 296;
+  a2a_scatter_rows_kernel<<<blocks, 256, 0, stream>>>(to_pp(s), offset,
+                                                      reinterpret_cast<const uint4*>(src), n_rows,
+                                                      vec_per_row, dst_rank, dst_row);
+}
+
+void launch_a2a_gather_rows(const SymmPeers& s, size_t offset, void* out, int n_rows, int hidden,
+                            const int* src_rank, const int* src_row, const float* scale,
+                            int accumulate, cudaStream_t stream) {
+  if (n_rows <= 0) return;
+  const int vec_per_row = hidden * 2 / 16;
+  int blocks = (n_rows + 7) / 8;
+  if (blocks > 296) blocks = 296;
+  a2a_gather_rows_kernel<<<blocks, 256, 0, stream>>>(to_pp(s), offset,
+                                                     reinterpret_cast<uint4*>(out), n_rows,
+                                                     vec_per_row, src_rank, src_row, scale,
+                                                     accumulate);
+}
+
+}  // namespace tdp

@@ -120,6 +120,7 @@ struct AdamWLaunch {
   float grad_scale;        // multiplied into grad (unscale / clip coefficient)
   const float* grad_scale_ptr;  // optional device scalar multiplied in as well
   void* param_copy_out;    // optional second bf16 destination (e.g. symmetric all-gather slot)
+  int adamw_mode;          // 1: decoupled weight decay (AdamW), 0: L2 added to the gradient (Adam)
 };
 void launch_adamw(const AdamWLaunch& a, cudaStream_t stream);
 

@@ -163,7 +163,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (p.comm_mode == COMM_AG_WAIT_A) {
           const int chunk = (m_blk * kBlockM) / p.rows_per_chunk;
           if (chunk != p.rank) {
-            while (ld_acquire_sys(p.chunk_flags + chunk) < p.flag_target) {
+            // wrap-safe "flag >= target" on monotonically increasing epochs
+            while (static_cast<int32_t>(ld_acquire_sys(p.chunk_flags + chunk) - p.flag_target) < 0) {
             }
             // peer / comm-CTA writes (generic proxy) -> our TMA reads (async proxy)
             fence_proxy_async_all();
@@ -394,7 +395,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         __syncwarp();
         if (lane == 0) {
           fence_acq_rel_sys();
-          red_add_release_sys(p.peer_tile_counter[dst_rank] + p.rank, 1u);
+          // unit = (32 rows x 8 columns): independent of the tile shape chosen by the host
+          red_add_release_sys(p.peer_tile_counter[dst_rank] + p.rank,
+                              static_cast<uint32_t>(min(BLOCK_N, p.N - n0) >> 3));
         }
       }
       if (++acc == 2) {

@@ -1,0 +1,425 @@
+"""ZeRO-1/2 style sharded optimizer ("hybrid ZeRO" when given an intra-node group).
+
+API parity with the reference ``Bf16ZeroOptimizer(optim, dp_group=None,
+bf16_master_weights=False, overlap_comm=False, stage=2, bucket_size=5e8, bucketize=True)``
+(ddp/zero_optim.py:98-315): wraps any elementwise torch optimizer, keeps fp32 master weights and
+optimizer state only for this rank's shard, reduces gradients during backward and re-distributes
+the updated parameters after ``step()``.
+
+B200-first redesign (what replaces the reference's all_reduce-then-discard + per-tensor
+broadcast, zero_optim.py:73-95,282-287):
+
+* All parameters of a param group live in one flat **symmetric-memory** buffer, in reverse
+  registration (= backward) order, cut into buckets of ``bucket_size`` elements.  Every bucket
+  is split evenly over the ranks: rank r owns slice r of every bucket (element-wise sharding, so
+  shards are perfectly balanced and a bucket's collective is a *true* reduce-scatter /
+  all-gather).
+* ``p.data`` and ``p.grad`` are views of the flat param / grad buffers -- no pack copies.
+* When a bucket's grads are complete, our NVLS reduce-scatter kernel (in-switch
+  ``multimem.ld_reduce`` of my slice) runs on a side stream and writes the averaged slice straight
+  into the **fp32 master gradient** (fused cast, csrc/coll/collectives.cu).
+* ``step()``: one fused Adam/AdamW kernel per bucket slice updates fp32 master + moments and
+  writes the bf16 result into this rank's slice of the flat param buffer (csrc/fused/optim.cu),
+  then the all-gather kernel (``multimem.st``: one store fans out to all peers) publishes it.
+  Other inner optimizers run their own ``step()`` on the fp32 shard followed by a cast kernel.
+* CPU / gloo fallback uses all_reduce + slice and ``dist.all_gather`` (tests, BASELINE config #1).
+* ``state_dict()`` / ``load_state_dict()`` exist (shard-local), which the reference lacks.
+
+Hybrid ZeRO: pass ``dp_group=setup_node_groups()`` and wrap the model in ``NaiveDDP`` over the
+inter-node group for the cross-node average (Intro.md:69-79 of the reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops._loader import native
+from ..ops.symm import get_symm_group
+from ..utils.flat import align_up
+
+
+class _ZBucket:
+    """A contiguous range of the flat buffers: [start, start + numel), numel = world * slice."""
+
+    def __init__(self, index: int, group_idx: int, start: int, numel: int, world: int):
+        self.index = index
+        self.group_idx = group_idx
+        self.start = start
+        self.numel = numel
+        self.slice = numel // world
+        self.params: List[torch.nn.Parameter] = []
+        self.ready = 0
+        self.reduced = False
+        self.work = None
+
+
+class Bf16ZeroOptimizer:
+    def __init__(self, optim: torch.optim.Optimizer, dp_group=None,
+                 bf16_master_weights: bool = False, overlap_comm: bool = False, stage: int = 2,
+                 bucket_size: float = 5e8, bucketize: bool = True, use_symm: Optional[bool] = None,
+                 grad_acc_steps: int = 1):
+        self.optim = optim
+        self.group = dp_group
+        self.world = dist.get_world_size(dp_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(dp_group) if dist.is_initialized() else 0
+        self.bf16_master_weights = bool(bf16_master_weights)
+        self.overlap_comm = bool(overlap_comm)
+        self.stage = int(stage)
+        self.bucketize = bool(bucketize)
+        self.grad_acc_steps = max(int(grad_acc_steps), 1)
+        self._micro = 0
+
+        first = self.optim.param_groups[0]["params"][0]
+        self.device = first.device
+        self.on_cuda = self.device.type == "cuda"
+        self.original_dtype = first.dtype
+        self.master_dtype = self.original_dtype if (self.bf16_master_weights or
+                                                    self.original_dtype == torch.float32) \
+            else torch.float32
+        self.separate_master = self.master_dtype != self.original_dtype
+        esize = first.element_size()
+        # every slice must be a multiple of 16 bytes for the vector kernels
+        self._slice_align = 128
+        bucket_numel = int(bucket_size) if self.bucketize else (1 << 62)
+        self.bucket_numel = max(align_up(bucket_numel, self.world * self._slice_align),
+                                self.world * self._slice_align)
+
+        self.comm_stream = None
+        if self.on_cuda:
+            _, hi = torch.cuda.Stream.priority_range()
+            self.comm_stream = torch.cuda.Stream(device=self.device, priority=hi)
+
+        self.model_param_groups: List[List[torch.nn.Parameter]] = []
+        self.buckets: List[_ZBucket] = []
+        self.flat_param: List[torch.Tensor] = []
+        self.flat_grad: List[torch.Tensor] = []
+        self.symm: List[Optional[tuple]] = []      # (SymmBuffer, param_off, grad_off) per group
+        self.master: List[torch.Tensor] = []       # fp32 shard (concatenated slices) per group
+        self.master_grad: List[torch.Tensor] = []
+        self._param_bucket: Dict[int, List[_ZBucket]] = {}
+        self._hooks = []
+        self._use_symm_req = use_symm
+        self._build()
+
+    # ------------------------------------------------------------------ construction
+    def _build(self) -> None:
+        for gi, pg in enumerate(self.optim.param_groups):
+            params = [p for p in pg["params"]]
+            self.model_param_groups.append(params)
+            for p in params:
+                if p.dtype != self.original_dtype:
+                    raise TypeError("Bf16ZeroOptimizer expects one parameter dtype "
+                                    f"({self.original_dtype}), found {p.dtype}")
+            order = list(reversed(params))          # backward order
+            # layout: params back to back (16-byte aligned starts), total padded to buckets
+            offsets, total = [], 0
+            for p in order:
+                total = align_up(total, 8)
+                offsets.append(total)
+                total += p.numel()
+            chunk = self.world * self._slice_align
+            if total <= self.bucket_numel:
+                total = align_up(max(total, chunk), chunk)
+                bucket_sizes = [total]
+            else:
+                n_full = total // self.bucket_numel
+                rem = total - n_full * self.bucket_numel
+                bucket_sizes = [self.bucket_numel] * n_full
+                if rem:
+                    bucket_sizes.append(align_up(rem, chunk))
+                total = sum(bucket_sizes)
+
+            esize = torch.empty((), dtype=self.original_dtype).element_size()
+            sym = None
+            if self.on_cuda and self.world > 1 and self._use_symm_req is not False \
+                    and self.original_dtype in (torch.bfloat16, torch.float32):
+                sg = get_symm_group(self.group)
+                if sg.enabled:
+                    nbytes = align_up(total * esize, 4096)
+                    sbuf = sg.alloc(2 * nbytes)
+                    sym = (sbuf, 0, nbytes)
+                elif self._use_symm_req:
+                    raise RuntimeError(f"symmetric memory unavailable: {sg.reason}")
+            if sym is not None:
+                flat_p = sym[0].view(sym[1], (total,), self.original_dtype)
+                flat_g = sym[0].view(sym[2], (total,), self.original_dtype)
+            else:
+                flat_p = torch.zeros(total, dtype=self.original_dtype, device=self.device)
+                flat_g = torch.zeros(total, dtype=self.original_dtype, device=self.device)
+            self.symm.append(sym)
+            self.flat_param.append(flat_p)
+            self.flat_grad.append(flat_g)
+
+            # buckets of this group
+            first_bucket = len(self.buckets)
+            start = 0
+            for bs in bucket_sizes:
+                self.buckets.append(_ZBucket(len(self.buckets), gi, start, bs, self.world))
+                start += bs
+            group_buckets = self.buckets[first_bucket:]
+
+            # re-home parameters and gradients into the flat buffers
+            with torch.no_grad():
+                for p, off in zip(order, offsets):
+                    view = flat_p[off:off + p.numel()].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view
+                    gview = flat_g[off:off + p.numel()].view(p.shape)
+                    if p.grad is not None:
+                        gview.copy_(p.grad)
+                    p.grad = gview if p.requires_grad else None
+                    p._zero_grad_view = gview
+                    touched = [b for b in group_buckets
+                               if b.start < off + p.numel() and off < b.start + b.numel]
+                    self._param_bucket[id(p)] = touched
+                    for b in touched:
+                        if p.requires_grad:
+                            b.params.append(p)
+
+            # this rank's shard = concatenation of slice `rank` of every bucket
+            shard_numel = sum(b.slice for b in group_buckets)
+            if self.separate_master:
+                master = torch.empty(shard_numel, dtype=torch.float32, device=self.device)
+                o = 0
+                for b in group_buckets:
+                    lo = b.start + self.rank * b.slice
+                    master[o:o + b.slice].copy_(flat_p[lo:lo + b.slice])
+                    o += b.slice
+                mgrad = torch.zeros(shard_numel, dtype=torch.float32, device=self.device)
+            else:
+                if len(group_buckets) == 1:
+                    b = group_buckets[0]
+                    lo = b.start + self.rank * b.slice
+                    master = flat_p[lo:lo + b.slice]
+                    mgrad = flat_g[lo:lo + b.slice] if self.world == 1 else torch.zeros_like(master)
+                else:
+                    # several buckets and no separate master: keep an explicit shard copy
+                    master = torch.cat([flat_p[b.start + self.rank * b.slice:
+                                               b.start + (self.rank + 1) * b.slice]
+                                        for b in group_buckets]).clone()
+                    mgrad = torch.zeros_like(master)
+                    self.separate_master = True
+                    self.master_dtype = master.dtype
+            master = torch.nn.Parameter(master, requires_grad=True) if not isinstance(
+                master, torch.nn.Parameter) else master
+            master.grad = mgrad
+            self.master.append(master)
+            self.master_grad.append(mgrad)
+            pg["params"] = [master]
+
+        for params in self.model_param_groups:
+            for p in params:
+                if p.requires_grad:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # ------------------------------------------------------------------ backward hooks
+    def _on_grad(self, p: torch.Tensor) -> None:
+        gview = p._zero_grad_view
+        if p.grad is not None and p.grad.data_ptr() != gview.data_ptr():
+            gview.copy_(p.grad)      # user dropped the view: re-attach
+            p.grad = gview
+        for b in self._param_bucket[id(p)]:
+            b.ready += 1
+            if b.ready >= len(b.params):
+                b.ready = 0
+                if self._micro + 1 >= self.grad_acc_steps and self.overlap_comm:
+                    self._reduce_bucket(b)
+
+    def _slice_of(self, b: _ZBucket, flat: torch.Tensor) -> torch.Tensor:
+        lo = b.start + self.rank * b.slice
+        return flat[lo:lo + b.slice]
+
+    def _master_slice(self, b: _ZBucket, t: torch.Tensor) -> torch.Tensor:
+        o = 0
+        for bb in self.buckets:
+            if bb.group_idx != b.group_idx:
+                continue
+            if bb is b:
+                return t[o:o + b.slice]
+            o += bb.slice
+        raise RuntimeError("bucket not found")
+
+    def _reduce_bucket(self, b: _ZBucket) -> None:
+        """Reduce-scatter bucket ``b``: averaged slice -> master grad (fp32)."""
+        if b.reduced:
+            return
+        b.reduced = True
+        gi = b.group_idx
+        flat_g = self.flat_grad[gi]
+        out = self._master_slice(b, self.master_grad[gi])
+        if self.world == 1:
+            if out.data_ptr() != self._slice_of(b, flat_g).data_ptr():
+                out.copy_(self._slice_of(b, flat_g))
+            return
+        sym = self.symm[gi]
+        if self.on_cuda:
+            cur = torch.cuda.current_stream(self.device)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                if sym is not None:
+                    esize = flat_g.element_size()
+                    sym[0].reduce_scatter(sym[2] + b.start * esize, b.slice, self.original_dtype,
+                                          out, scale=1.0 / self.world)
+                else:
+                    seg = flat_g[b.start:b.start + b.numel]
+                    tmp = torch.empty(b.slice, dtype=seg.dtype, device=seg.device)
+                    dist.reduce_scatter_tensor(tmp, seg, op=dist.ReduceOp.AVG, group=self.group)
+                    out.copy_(tmp)
+        else:
+            seg = flat_g[b.start:b.start + b.numel]
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            out.copy_(self._slice_of(b, flat_g))
+            out.div_(self.world)
+
+    def finish_bucket(self) -> None:
+        """Flush reductions that did not fire from the hooks (no overlap, unused params)."""
+        for b in self.buckets:
+            self._reduce_bucket(b)
+
+    # ------------------------------------------------------------------ step
+    def _fused_adam_ok(self, gi: int) -> bool:
+        return (self.on_cuda and native() is not None and self.separate_master
+                and self.original_dtype == torch.bfloat16
+                and type(self.optim) in (torch.optim.AdamW, torch.optim.Adam)
+                and not self.optim.param_groups[gi].get("amsgrad", False)
+                and not self.optim.param_groups[gi].get("maximize", False))
+
+    def step(self, closure=None):
+        self._micro += 1
+        if self._micro < self.grad_acc_steps:
+            return None
+        self._micro = 0
+        self.finish_bucket()
+        if self.on_cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+
+        for gi, pg in enumerate(self.optim.param_groups):
+            master = self.master[gi]
+            flat_p = self.flat_param[gi]
+            gb = [b for b in self.buckets if b.group_idx == gi]
+            if self._fused_adam_ok(gi):
+                C = native()
+                st = self.optim.state[master]
+                if "step" not in st:
+                    st["step"] = torch.zeros((), dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(master.data)
+                    st["exp_avg_sq"] = torch.zeros_like(master.data)
+                st["step"] += 1
+                step = int(st["step"].item()) if torch.is_tensor(st["step"]) else int(st["step"])
+                beta1, beta2 = pg["betas"]
+                adamw = isinstance(self.optim, torch.optim.AdamW) or bool(
+                    pg.get("decoupled_weight_decay", False))
+                for b in gb:
+                    C.adamw(self._slice_of(b, flat_p), self._master_slice(b, master.data),
+                            self._master_slice(b, master.grad),
+                            self._master_slice(b, st["exp_avg"]),
+                            self._master_slice(b, st["exp_avg_sq"]), float(pg["lr"]), beta1, beta2,
+                            float(pg["eps"]), float(pg["weight_decay"]), step, adamw, 1.0, None,
+                            None)
+            else:
+                pass
+        if not all(self._fused_adam_ok(gi) for gi in range(len(self.optim.param_groups))):
+            # generic inner optimizer on the fp32 shards (groups already handled above are
+            # skipped by temporarily hiding their grads)
+            hidden = []
+            for gi in range(len(self.optim.param_groups)):
+                if self._fused_adam_ok(gi):
+                    hidden.append((self.master[gi], self.master[gi].grad))
+                    self.master[gi].grad = None
+            self.optim.step()
+            for m, g in hidden:
+                m.grad = g
+            for gi in range(len(self.optim.param_groups)):
+                if self._fused_adam_ok(gi) or not self.separate_master:
+                    continue
+                for b in (bb for bb in self.buckets if bb.group_idx == gi):
+                    self._slice_of(b, self.flat_param[gi]).copy_(
+                        self._master_slice(b, self.master[gi].data))
+
+        self._all_gather_params()
+        for b in self.buckets:
+            b.reduced = False
+            b.ready = 0
+        return None
+
+    def _all_gather_params(self) -> None:
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            gi = b.group_idx
+            flat_p = self.flat_param[gi]
+            sym = self.symm[gi]
+            if sym is not None:
+                esize = flat_p.element_size()
+                sym[0].all_gather(sym[1] + b.start * esize, b.slice * esize, None)
+            else:
+                seg = flat_p[b.start:b.start + b.numel]
+                mine = self._slice_of(b, flat_p).clone()
+                if self.on_cuda:
+                    dist.all_gather_into_tensor(seg, mine, group=self.group)
+                else:
+                    outs = [seg[r * b.slice:(r + 1) * b.slice] for r in range(self.world)]
+                    tmp = [torch.empty_like(mine) for _ in range(self.world)]
+                    dist.all_gather(tmp, mine, group=self.group)
+                    for o, t in zip(outs, tmp):
+                        o.copy_(t)
+
+    # ------------------------------------------------------------------ optimizer protocol
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Zero the model gradients in place (bucket views stay attached) and the master grads."""
+        for g in self.flat_grad:
+            g.zero_()
+        for mg in self.master_grad:
+            mg.zero_()
+
+    @property
+    def state(self):
+        return self.optim.state
+
+    @property
+    def param_groups(self):
+        return self.optim.param_groups
+
+    @param_groups.setter
+    def param_groups(self, value):
+        self.optim.param_groups = value
+
+    def state_dict(self) -> dict:
+        """Shard-local state: inner optimizer state (fp32 moments of this rank's shard), the fp32
+        master shard and the layout needed to validate a reload."""
+        return {
+            "optimizer": self.optim.state_dict(),
+            "master": [m.data.detach().clone().cpu() for m in self.master],
+            "layout": {"world": self.world, "rank": self.rank,
+                       "buckets": [(b.group_idx, b.start, b.numel) for b in self.buckets]},
+        }
+
+    def load_state_dict(self, sd: dict) -> None:
+        lay = sd["layout"]
+        if lay["world"] != self.world or lay["rank"] != self.rank or \
+                [tuple(x) for x in lay["buckets"]] != [(b.group_idx, b.start, b.numel)
+                                                       for b in self.buckets]:
+            raise ValueError("ZeRO checkpoint layout does not match this run")
+        self.optim.load_state_dict(sd["optimizer"])
+        with torch.no_grad():
+            for gi, (m, saved) in enumerate(zip(self.master, sd["master"])):
+                m.data.copy_(saved.to(m.device))
+                for b in (bb for bb in self.buckets if bb.group_idx == gi):
+                    self._slice_of(b, self.flat_param[gi]).copy_(self._master_slice(b, m.data))
+        self._all_gather_params()
+
+    # grad-norm support (used by clip_grad_norm_): squared L2 norm of this rank's shard
+    def local_grad_sq_norm(self) -> torch.Tensor:
+        self.finish_bucket()
+        if self.on_cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        for mg in self.master_grad:
+            total = total + mg.float().pow(2).sum()
+        return total
+
+    def scale_master_grads(self, coef) -> None:
+        for mg in self.master_grad:
+            mg.mul_(coef)

@@ -1,0 +1,155 @@
+"""Symmetric memory over NVSwitch: same-size buffers on every rank of a process group, each
+rank holding peer-mapped pointers to all of them, one NVLS multicast mapping, and a signal pad
+for in-kernel flags.  The collectives and the fused GEMM+collective kernels of this package
+address these pointers directly (csrc/coll/collectives.cu, csrc/gemm/gemm_sm100.cuh).
+
+Handle exchange (CUDA VMM export/import + multicast bind) is delegated to
+``torch.distributed._symmetric_memory``; everything that moves data is our own kernel.
+
+Signal pad word layout (uint32 words, see collectives.cu):
+    [0, 1536)        barrier slots owned by the collective kernels
+    [2048, ...)      user words: chunk flags / tile counters, handed out by ``alloc_words``
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._loader import native
+
+SIGNAL_PAD_BYTES = 64 * 1024
+USER_WORD_BASE = 2048
+_MAX_WORLD = 8
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.bfloat16:
+        return 0
+    if dtype == torch.float32:
+        return 1
+    raise TypeError(f"symmetric collectives support bf16 / fp32, got {dtype}")
+
+
+class SymmBuffer:
+    """One symmetric allocation.  ``tensor`` is this rank's memory (uint8)."""
+
+    def __init__(self, group: "SymmGroup", nbytes: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group
+        self.nbytes = int(nbytes)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.tensor = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(self.tensor, group.pg)
+        self._torch_handle = hdl
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if group.disable_multicast:
+            mc = 0
+        self.handle = native(required=True).SymmHandle(
+            [int(p) for p in hdl.buffer_ptrs], [int(p) for p in hdl.signal_pad_ptrs], mc,
+            int(hdl.rank), int(hdl.world_size), self.nbytes, dev.index)
+        self.has_multicast = bool(mc)
+        self._next_word = USER_WORD_BASE
+        self._epochs: Dict[int, int] = {}
+        self.tensor.zero_()
+        # all ranks must have finished initialising before anyone pushes data
+        torch.cuda.synchronize()
+        dist.barrier(group=group.pg)
+
+    # ---------------------------------------------------------------- views
+    def view(self, offset: int, shape, dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        assert offset % 16 == 0 and offset + nb <= self.nbytes, "symmetric view out of range"
+        return self.tensor[offset:offset + nb].view(dtype).view(*shape)
+
+    def alloc_words(self, n: int) -> int:
+        """Reserve ``n`` uint32 words of the signal pad (same index on every rank)."""
+        w = self._next_word
+        self._next_word += int(n)
+        assert self._next_word * 4 <= SIGNAL_PAD_BYTES, "signal pad exhausted"
+        return w
+
+    def next_epoch(self, word: int, step: int = 1) -> int:
+        """Monotonic per-flag epoch kept in lock step on all ranks by construction."""
+        e = (self._epochs.get(word, 0) + step) & 0xFFFFFFFF
+        self._epochs[word] = e
+        return e
+
+    # ---------------------------------------------------------------- collectives (in place)
+    def barrier(self, slot: int = 0) -> None:
+        self.handle.barrier(slot)
+
+    def all_reduce_(self, offset: int, numel: int, dtype: torch.dtype, scale: float = 1.0,
+                    algo: int = 0, max_ctas: int = 0) -> None:
+        self.handle.all_reduce(offset, numel, _dtype_code(dtype), scale, algo, max_ctas)
+
+    def reduce_scatter(self, offset: int, slice_numel: int, dtype: torch.dtype, out: torch.Tensor,
+                       scale: float = 1.0, accumulate: bool = False, max_ctas: int = 0) -> None:
+        self.handle.reduce_scatter(offset, slice_numel, _dtype_code(dtype), scale, out, accumulate,
+                                   True, max_ctas)
+
+    def all_gather(self, offset: int, slice_bytes: int, src: Optional[torch.Tensor] = None,
+                   max_ctas: int = 0) -> None:
+        self.handle.all_gather(offset, slice_bytes, src, True, max_ctas)
+
+
+class SymmGroup:
+    """Symmetric-memory context of one process group (NVSwitch domain, <= 8 ranks)."""
+
+    def __init__(self, pg=None, disable_multicast: bool = False):
+        self.pg = pg if pg is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.pg)
+        self.world = dist.get_world_size(self.pg)
+        self.disable_multicast = disable_multicast
+        self.enabled = False
+        self.reason = ""
+        self._buffers: List[SymmBuffer] = []
+        if not torch.cuda.is_available() or dist.get_backend(self.pg) != "nccl":
+            self.reason = "no CUDA / not an NCCL group"
+            return
+        if self.world < 2 or self.world > _MAX_WORLD:
+            self.reason = f"group size {self.world} outside [2, {_MAX_WORLD}]"
+            return
+        if native() is None:
+            self.reason = "native extension missing"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            try:
+                symm_mem.set_signal_pad_size(SIGNAL_PAD_BYTES)
+            except Exception:
+                pass
+            try:
+                symm_mem.enable_symm_mem_for_group(self.pg.group_name)
+            except Exception:
+                pass
+            self.enabled = True
+        except Exception as e:  # pragma: no cover - depends on the torch build
+            self.reason = f"symmetric memory unavailable: {e}"
+
+    def alloc(self, nbytes: int) -> SymmBuffer:
+        if not self.enabled:
+            raise RuntimeError(f"symmetric memory not available for this group: {self.reason}")
+        nbytes = (int(nbytes) + 2 * 1024 * 1024 - 1) // (2 * 1024 * 1024) * (2 * 1024 * 1024)
+        buf = SymmBuffer(self, nbytes)
+        self._buffers.append(buf)
+        return buf
+
+
+_GROUP_CACHE: Dict[int, SymmGroup] = {}
+
+
+def get_symm_group(pg=None) -> SymmGroup:
+    """One :class:`SymmGroup` per process group (cached)."""
+    key = id(pg if pg is not None else dist.group.WORLD)
+    if key not in _GROUP_CACHE:
+        _GROUP_CACHE[key] = SymmGroup(pg)
+    return _GROUP_CACHE[key]
+
+
+def reset_symm_cache() -> None:
+    _GROUP_CACHE.clear()
