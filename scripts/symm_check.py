@@ -143,7 +143,7 @@ def run_ag_gemm():
     buf.barrier(2)
     ep = buf.next_epoch(flag_word)
     buf.handle.all_gather_signal(ag_off, rows * Kf * 2, xs, flag_word, ep, True, 16)
-    buf.handle.gemm_ag(ag_off, rows, Kf, w2, False, cfull, None, None, 0, flag_word, ep, 0)
+    buf.handle.gemm_ag(ag_off, rows, Kf, w2, False, cfull, None, None, 0, flag_word, ep, 0, xs, None)
 try:
     run_ag_gemm()
     gl = [torch.empty_like(xs) for _ in range(world)]

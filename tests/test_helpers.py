@@ -1,0 +1,192 @@
+"""Single-process CPU tests: pure helpers, tools, CPU fall-backs of the operator layer."""
+import copy
+import io
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import torchdistpackage_b200 as tdp
+from torchdistpackage_b200.parallel.pipeline_parallel.pipeline_helper import (
+    balanced_bounds, uniform_bounds, flatten_model, flatten_sequence, CallableModule)
+from torchdistpackage_b200.utils import greedy_partition_sizes, partition_params
+
+
+def test_uniform_and_balanced_bounds():
+    assert uniform_bounds(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    assert uniform_bounds(5, 2, extra_len=1) == [(0, 3), (3, 5)]
+    b = balanced_bounds([10, 1, 1, 1, 1, 10], 3)
+    assert b[0][0] == 0 and b[-1][1] == 6 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+    assert max(sum([10, 1, 1, 1, 1, 10][a:c]) for a, c in b) == 10 + 1 or \
+        max(sum([10, 1, 1, 1, 1, 10][a:c]) for a, c in b) <= 12
+    # more parts than the bottleneck search needs -> still n non-empty parts
+    b = balanced_bounds([5, 5, 5, 5], 4)
+    assert b == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    b = balanced_bounds([1, 1, 1, 100], 3)
+    assert len(b) == 3 and all(c > a for a, c in b)
+
+
+def test_flatten_model_and_sequence():
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(4, 4)
+            self.seq = nn.Sequential(nn.ReLU(), nn.Linear(4, 4))
+            self.head = nn.Linear(4, 2)
+
+        def forward(self, x):
+            return self.head(self.seq(self.a(x)).flatten(1))
+
+    net = Net()
+    flat = flatten_model(net, ["a", "seq", lambda t: t.flatten(1), "head"])
+    assert len(flat) == 5 and isinstance(flat[3], CallableModule)
+    x = torch.randn(3, 4)
+    assert torch.allclose(flat(x), net(x))
+    nested = nn.Sequential(nn.Sequential(nn.ReLU(), nn.ReLU()), nn.Tanh())
+    assert len(flatten_sequence(nested, 1)) == 3
+    assert len(flatten_sequence(nested, 0)) == 2
+
+
+def test_partition_params_and_fix_rand():
+    owners = greedy_partition_sizes([10, 10, 10, 10], 2)
+    assert owners == [0, 0, 1, 1]
+    owners = greedy_partition_sizes([100, 1, 1, 1], 3)
+    assert owners[0] == 0 and max(owners) <= 2
+    m = nn.Sequential(nn.Linear(8, 8), nn.Linear(8, 8), nn.Linear(8, 2))
+    parts = partition_params(m, 2, return_dict=True)
+    assert sum(len(p) for p in parts) == 6 and all(len(p) > 0 for p in parts)
+    tdp.fix_rand(3)
+    a = torch.rand(4)
+    tdp.fix_rand(3)
+    assert torch.equal(a, torch.rand(4))
+
+
+def test_module_profiler_and_replace(capsys):
+    model = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Sequential(nn.Linear(16, 16), nn.Linear(16, 4)))
+    prof = tdp.get_model_profile(model, args=(torch.randn(2, 8),), sort=True, max_depth=2)
+    out = capsys.readouterr().out
+    assert "level 0" in out and "level 1" in out and 1 in prof and len(prof[1]) == 3
+    handles = tdp.register_profile_hooks(model)
+    model(torch.randn(2, 8))
+    rep = tdp.report_prof(topn=2)
+    assert len(rep[1]) == 2
+    from torchdistpackage_b200.tools import remove_profile_hooks
+    remove_profile_hooks()
+    tdp.replace_all_module(model, lambda m: isinstance(m, nn.ReLU), lambda m: nn.GELU())
+    assert isinstance(model[1], nn.GELU)
+    from torchdistpackage_b200.tools.module_profiler import get_dt_size
+    assert get_dt_size(torch.int8) == 1 and get_dt_size(torch.bfloat16) == 2
+
+
+def test_nan_hooks():
+    from torchdistpackage_b200.tools.debug_nan import register_nan_hooks, check_model_params, check_tensors
+    model = nn.Sequential(nn.Linear(4, 4), nn.ReLU())
+    register_nan_hooks(model)
+    model(torch.randn(2, 4))
+    with pytest.raises(FloatingPointError):
+        model(torch.full((2, 4), float("nan")))
+    assert not check_model_params(model)
+    assert check_tensors([torch.tensor([1.0, float("inf")])], "x")
+
+
+def test_dist_utils_and_comm_formula():
+    from torchdistpackage_b200.dist.utils import (NVTXContext, nvtx_decorator, _has_inf_or_nan,
+                                                  disable_non_master_print, restore_print)
+    from torchdistpackage_b200.dist.py_comm_test import bus_bandwidth_gbs
+    with NVTXContext("blk", record_time=False):
+        pass
+
+    @nvtx_decorator("f")
+    def f(x):
+        return x + 1
+    assert f(1) == 2
+    assert _has_inf_or_nan(torch.tensor([float("nan")])) and not _has_inf_or_nan(torch.ones(3))
+    disable_non_master_print(False)
+    try:
+        print("hidden")
+        print("shown", force=True)
+    finally:
+        restore_print()
+    assert abs(bus_bandwidth_gbs("all_reduce", 10 ** 9, 1.0, 8) - 2 * 7 / 8) < 1e-9
+    assert abs(bus_bandwidth_gbs("all_gather", 10 ** 9, 1.0, 8) - 7 / 8) < 1e-9
+
+
+def test_slurm_monitor_resubmits():
+    from torchdistpackage_b200.tools.slurm_job_monitor import monitor_job
+    states = iter(["RUNNING", "FAILED", "PENDING", "RUNNING", "COMPLETED"])
+    jobs = iter(["11", "12"])
+    calls = []
+
+    def runner(cmd):
+        calls.append(cmd[0])
+        if cmd[0] == "sbatch":
+            return f"Submitted batch job {next(jobs)}"
+        return next(states)
+    n = monitor_job("job.sh", interval=0, runner=runner, sleep=lambda s: None)
+    assert n == 2 and calls.count("sbatch") == 2
+
+
+def test_setup_distributed_single_process_and_ckpt_suffix(monkeypatch):
+    for k in ("RANK", "WORLD_SIZE", "SLURM_JOB_ID", "SLURM_PROCID", "MASTER_PORT"):
+        monkeypatch.delenv(k, raising=False)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    rank, world, port, addr = tdp.setup_distributed("gloo")
+    assert (rank, world, addr) == (0, 1, "127.0.0.1") and port > 0
+    tdp.tpc.reset()
+    tdp.tpc.verbose = False
+    tdp.tpc.setup_process_groups([("data", 1)])
+    assert tdp.get_mp_ckpt_suffix() == ".pth" and not tdp.is_using_pp()
+    assert tdp.test_comm(verbose=False)
+    tdp.shutdown_distributed()
+
+
+def test_ops_cpu_fallbacks_match_torch():
+    from torchdistpackage_b200.ops import linear as L, fused
+    torch.manual_seed(0)
+    x = torch.randn(5, 8, requires_grad=True)
+    w = torch.randn(8, 6, requires_grad=True)
+    b = torch.randn(6, requires_grad=True)
+    assert torch.allclose(L.linear(x, w, b, act="gelu"), F.gelu(x @ w + b), atol=1e-6)
+    assert torch.allclose(L.linear(x, w.t().contiguous(), b, layout="nk"), x @ w + b, atol=1e-6)
+    w2 = torch.randn(6, 8)
+    assert torch.allclose(L.mlp(x, w, b, w2, None, act="gelu_tanh", residual=x),
+                          F.gelu(x @ w + b, approximate="tanh") @ w2 + x, atol=1e-5)
+    y, s = fused.layer_norm(x, torch.ones(8), torch.zeros(8), 1e-5, residual=x)
+    assert torch.allclose(s, 2 * x) and torch.allclose(y, F.layer_norm(2 * x, (8,)), atol=1e-6)
+    logits = torch.randn(7, 11, requires_grad=True)
+    t = torch.randint(0, 11, (7,))
+    assert torch.allclose(fused.cross_entropy(logits, t), F.cross_entropy(logits, t))
+
+
+def test_fused_adamw_cpu_matches_torch():
+    from torchdistpackage_b200.ops.fused import FusedAdamW
+    torch.manual_seed(0)
+    p = nn.Parameter(torch.randn(33))
+    q = nn.Parameter(p.detach().clone())
+    a = FusedAdamW([p], lr=1e-2, weight_decay=0.1)
+    b = torch.optim.AdamW([q], lr=1e-2, weight_decay=0.1)
+    for _ in range(3):
+        g = torch.randn(33)
+        p.grad, q.grad = g.clone(), g.clone()
+        a.step(); b.step()
+    assert torch.allclose(p, q, atol=1e-6)
+
+
+def test_gpt2_config_counts():
+    from torchdistpackage_b200.models.gpt2 import GPT2Config, build_gpt2
+    c = GPT2Config.small()
+    m = build_gpt2("tiny", dtype=torch.float32)
+    assert sum(p.numel() for p in m.parameters()) == GPT2Config.tiny().num_params()
+    assert 120e6 < c.num_params() < 130e6 and c.flops_per_token() > 6 * 85e6
+
+
+def test_graft_entry_build_contract():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as g
+    assert callable(g.build) and callable(g.smoke)

@@ -3,6 +3,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
 
+#include <atomic>
 #include <optional>
 #include <vector>
 
@@ -14,6 +15,10 @@ using torch::Tensor;
 using OptTensor = std::optional<Tensor>;
 
 inline cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+
+// number of kernels of this extension launched so far (bench.py reports the per-step delta)
+std::atomic<int64_t> g_launches{0};
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 inline const void* opt_ptr(const OptTensor& t) {
   return (t.has_value() && t->defined()) ? t->data_ptr() : nullptr;
@@ -77,6 +82,7 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& c, bool trans_a, bool trans_
   g.block_n = static_cast<int>(block_n);
   g.max_ctas = static_cast<int>(max_ctas);
   const char* err = nullptr;
+  count_launch();
   int rc = tdp::launch_gemm_bf16(g, cur_stream(), &err);
   TORCH_CHECK(rc == 0, "tdp gemm failed (", rc, "): ", err ? err : "");
 }
@@ -93,5 +99,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("accumulate") = false, py::arg("alpha") = 1.0, py::arg("block_n") = 0,
         py::arg("max_ctas") = 0);
   m.def("num_sms", &tdp::gemm_num_sms);
+  m.def("launch_count", []() { return g_launches.load(); });
   register_ext(m);
 }

@@ -135,16 +135,30 @@ all_reduce_two_shot_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int ra
   const size_t per = (n_vec + world - 1) / world;
   const size_t lo = min(per * rank, n_vec), hi = min(lo + per, n_vec);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  // kUnroll independent 16-byte reductions in flight per thread: NVLink round trips are ~2-4 us,
+  // bandwidth = bytes in flight / latency.
+  constexpr int kUnroll = kMc ? 8 : 4;
   for (size_t i = lo + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hi;
-       i += stride) {
-    const size_t off = offset + i * 16;
-    const uint4 v = reduce16<kMc, kFp32>(pp, mc, world, off, scale);
-    if constexpr (kMc) {
-      multimem_st_v4(mc + off, v);
-    } else {
+       i += stride * kUnroll) {
+    uint4 v[kUnroll];
 #pragma unroll
-      for (int p = 0; p < kApiMaxPeers; ++p)
-        if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + off, v);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx < hi) v[u] = reduce16<kMc, kFp32>(pp, mc, world, offset + idx * 16, scale);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx < hi) {
+        const size_t off = offset + idx * 16;
+        if constexpr (kMc) {
+          multimem_st_v4(mc + off, v[u]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < kApiMaxPeers; ++p)
+            if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + off, v[u]);
+        }
+      }
     }
   }
   block_barrier(pp, rank, world, slot_base + kBarrierSlotWords);
@@ -161,9 +175,20 @@ reduce_scatter_kernel(const __grid_constant__ PeerPtrs pp, const char* mc, int r
   block_barrier(pp, rank, world, slot_base);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t base = offset + static_cast<size_t>(rank) * slice_vec * 16;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slice_vec;
-       i += stride) {
-    const uint4 v = reduce16<kMc, kFp32In>(pp, mc, world, base + i * 16, scale);
+  constexpr int kUnroll = kMc ? 8 : 4;
+  for (size_t i0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < slice_vec;
+       i0 += stride * kUnroll) {
+   uint4 vv[kUnroll];
+#pragma unroll
+   for (int u = 0; u < kUnroll; ++u) {
+     const size_t idx = i0 + u * stride;
+     if (idx < slice_vec) vv[u] = reduce16<kMc, kFp32In>(pp, mc, world, base + idx * 16, scale);
+   }
+#pragma unroll
+   for (int u = 0; u < kUnroll; ++u) {
+    const size_t i = i0 + u * stride;
+    if (i >= slice_vec) break;
+    const uint4 v = vv[u];
     if constexpr (kFp32In) {
       float4 f = *reinterpret_cast<const float4*>(&v);
       float4* o = reinterpret_cast<float4*>(out) + i;
@@ -190,6 +215,7 @@ reduce_scatter_kernel(const __grid_constant__ PeerPtrs pp, const char* mc, int r
         *o = v;
       }
     }
+   }
   }
   block_barrier(pp, rank, world, slot_base + kBarrierSlotWords);
 }
@@ -232,15 +258,27 @@ all_gather_signal_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank
                          uint32_t* ticket) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t base = offset + static_cast<size_t>(rank) * slice_vec * 16;
+  constexpr int kUnroll = 8;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slice_vec;
-       i += stride) {
-    const uint4 v = src[i];
-    if constexpr (kMc) {
-      multimem_st_v4(mc + base + i * 16, v);
-    } else {
+       i += stride * kUnroll) {
+    uint4 v[kUnroll];
 #pragma unroll
-      for (int p = 0; p < kApiMaxPeers; ++p)
-        if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + base + i * 16, v);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx < slice_vec) v[u] = ld_nc_v4(src + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx < slice_vec) {
+        if constexpr (kMc) {
+          multimem_st_v4(mc + base + idx * 16, v[u]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < kApiMaxPeers; ++p)
+            if (p < world) st_na_v4(reinterpret_cast<char*>(pp.buf[p]) + base + idx * 16, v[u]);
+        }
+      }
     }
   }
   __syncthreads();

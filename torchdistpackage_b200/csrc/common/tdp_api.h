@@ -34,6 +34,8 @@ struct GemmLaunch {
   int comm_mode;
   int rank, world;
   int rows_per_chunk;
+  const void* a_local;   // AG mode: this rank's un-gathered shard [rows_per_chunk, lda_local]
+  int lda_local;
   uint32_t* chunk_flags;
   uint32_t flag_target;
   void* peer_out[kApiMaxPeers];

@@ -69,7 +69,22 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return false;
+  if (r != CUDA_SUCCESS) {
+    // worker threads (autograd engine) may not have a current context yet: bind it and retry
+    cudaFree(nullptr);
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr,
+            "[tdp] cuTensorMapEncodeTiled failed: CUresult=%d base=%p dims={%llu,%llu} ld=%llu "
+            "box={%u,%u}\n",
+            static_cast<int>(r), base, static_cast<unsigned long long>(inner),
+            static_cast<unsigned long long>(outer), static_cast<unsigned long long>(ld), box_inner,
+            box_outer);
+    return false;
+  }
   std::lock_guard<std::mutex> lk(mu);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, *out);
@@ -79,8 +94,9 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
 int g_num_sms = 0;
 
 template <int BLOCK_N>
-cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                        int grid, cudaStream_t stream) {
+cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta_local,
+                        const GemmStoreMaps& sm, const GemmParams& p, int grid,
+                        cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -90,7 +106,8 @@ cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, p);
+  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, ta_local,
+                                                                                  sm, p);
   return cudaGetLastError();
 }
 
@@ -161,10 +178,7 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
   p.rows_per_chunk = g.rows_per_chunk;
   p.chunk_flags = g.chunk_flags;
   p.flag_target = g.flag_target;
-  for (int i = 0; i < kMaxPeers; ++i) {
-    p.peer_out[i] = g.peer_out[i];
-    p.peer_tile_counter[i] = g.peer_tile_counter[i];
-  }
+  for (int i = 0; i < kMaxPeers; ++i) p.peer_tile_counter[i] = g.peer_tile_counter[i];
   if (p.comm_mode != COMM_NONE) {
     if (g.world < 1 || g.world > kMaxPeers || g.rows_per_chunk % kBlockM != 0 ||
         g.rows_per_chunk * g.world != g.M) {
@@ -188,10 +202,43 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
   else            ok = make_tmap_2d(&tb, g.b, g.N, g.K, g.ldb, 64, kBlockK);
   if (!ok) { snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(B) failed"); return -2; }
 
+  // local (un-gathered) A shard for the all-gather variant: zero-copy, never waits
+  CUtensorMap ta_local = ta;
+  p.has_a_local = 0;
+  if (p.comm_mode == COMM_AG_WAIT_A && g.a_local != nullptr && !g.trans_a) {
+    if (!make_tmap_2d(&ta_local, g.a_local, g.K, g.rows_per_chunk, g.lda_local, kBlockK, kBlockM)) {
+      snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(A local) failed");
+      return -2;
+    }
+    p.has_a_local = 1;
+  }
+
+  // output maps: bf16 results leave through swizzled smem + TMA store (128 x 64 boxes)
+  GemmStoreMaps sm;
+  memset(&sm, 0, sizeof(sm));
+  p.use_tma_store = 0;
+  if (p.comm_mode == COMM_RS_SCATTER) {
+    for (int r = 0; r < g.world; ++r) {
+      const char* base = reinterpret_cast<const char*>(g.peer_out[r]) +
+                         static_cast<size_t>(g.rank) * g.rows_per_chunk * g.ldc * 2;
+      if (!make_tmap_2d(&sm.m[r], base, g.N, g.rows_per_chunk, g.ldc, kStoreCols, kBlockM)) {
+        snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(peer C) failed");
+        return -2;
+      }
+    }
+    p.use_tma_store = 1;
+  } else if (!g.c_fp32 && !g.accumulate && (reinterpret_cast<uintptr_t>(g.c) & 15) == 0) {
+    if (!make_tmap_2d(&sm.m[0], g.c, g.N, g.M, g.ldc, kStoreCols, kBlockM)) {
+      snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(C) failed");
+      return -2;
+    }
+    p.use_tma_store = 1;
+  }
+
   const long tiles = static_cast<long>(p.num_m_blocks) * p.num_n_blocks;
   const int grid = static_cast<int>(tiles < max_ctas ? tiles : max_ctas);
-  cudaError_t e = (block_n == 256) ? launch_impl<256>(ta, tb, p, grid, stream)
-                                   : launch_impl<128>(ta, tb, p, grid, stream);
+  cudaError_t e = (block_n == 256) ? launch_impl<256>(ta, tb, ta_local, sm, p, grid, stream)
+                                   : launch_impl<128>(ta, tb, ta_local, sm, p, grid, stream);
   if (e != cudaSuccess) {
     snprintf(msg, sizeof(msg), "gemm launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);

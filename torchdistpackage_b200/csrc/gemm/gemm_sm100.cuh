@@ -1,12 +1,13 @@
 // Warp-specialised persistent bf16 GEMM for sm_100a:
 //   TMA (128B swizzle) -> smem ring -> tcgen05.mma (single elected thread, cta_group::1, M=128)
 //   -> fp32 accumulators in TMEM (double buffered) -> tcgen05.ld epilogue with fused
-//   bias / GELU / dGELU / residual / accumulate / peer-scatter.
+//   bias / GELU / dGELU / residual / accumulate -> swizzled smem staging -> TMA store
+//   (to local memory, or straight into a peer GPU's staging buffer over NVLink).
 //
-// This header is the shared main loop.  Plain GEMM (gemm.cu) and the GEMM+collective kernels
-// (gemm_comm.cu: all-gather->GEMM, GEMM->reduce-scatter, GEMM->all-reduce) instantiate it with
-// different tile-order / producer-wait / epilogue-destination policies selected at run time
-// through GemmParams (all branches are warp uniform).
+// This header is the shared main loop.  Plain GEMM and the GEMM+collective variants
+// (all-gather->GEMM, GEMM->reduce-scatter, GEMM->all-reduce) are the same kernel with different
+// tile-order / producer-wait / epilogue-destination policies selected at run time through
+// GemmParams (all branches are warp uniform).
 //
 // Replaces the reference's torch.matmul(x, W) + in-place bias (tensor_parallel/tp_utils.py:170-174)
 // and, in the fused variants, the collective that follows/precedes it (tp_utils.py:44,67,84).
@@ -21,6 +22,8 @@ constexpr int kUmmaK = 16;
 constexpr int kNumEpilogueWarps = 4;
 constexpr int kGemmThreads = 32 * (2 + kNumEpilogueWarps);  // warp0 TMA, warp1 MMA, warps2-5 epi
 constexpr int kMaxPeers = 8;
+constexpr int kStoreCols = 64;                         // TMA-store sub-tile: 128 rows x 64 cols
+constexpr int kStoreBytes = kBlockM * kStoreCols * 2;  // 16 KiB, 128B-swizzled
 
 enum GemmAct : int {
   ACT_NONE = 0,
@@ -33,10 +36,11 @@ enum GemmAct : int {
 enum GemmCommMode : int {
   COMM_NONE = 0,
   // A operand rows arrive chunk by chunk (all-gather): the TMA producer waits on
-  // chunk_flags[chunk] >= flag_target before loading A rows of that chunk.
+  // chunk_flags[chunk] >= flag_target before loading A rows of a remote chunk; the local chunk
+  // is read straight from the un-gathered shard (tmap_a_local), so it never waits.
   COMM_AG_WAIT_A = 1,
-  // C rows are partial sums destined for the rank that owns the row chunk: the epilogue stores
-  // the tile into that rank's staging buffer (peer memory) and bumps its per-chunk counter.
+  // C rows are partial sums destined for the rank that owns the row chunk: the epilogue TMA-stores
+  // the tile into that rank's staging buffer (peer memory) and bumps its per-source counter.
   COMM_RS_SCATTER = 2,
 };
 
@@ -49,6 +53,7 @@ struct GemmParams {
   int ldc;
   int c_fp32;
   int accumulate;   // C += result (fp32 or bf16 read-modify-write)
+  int use_tma_store;
   float alpha;
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, ld_res] or null
@@ -62,11 +67,15 @@ struct GemmParams {
   int comm_mode;
   int rank, world;
   int rows_per_chunk;             // M / world (chunk c belongs to rank c)
+  int has_a_local;
   uint32_t* chunk_flags;          // [world] local flags (AG wait) -- device memory of this rank
   uint32_t flag_target;           // monotonically increasing epoch value
-  // RS scatter: peer_out[r] = base of rank r's staging buffer [world][rows_per_chunk][ldc] bf16
-  void* peer_out[kMaxPeers];
-  uint32_t* peer_tile_counter[kMaxPeers];  // per-rank counter array [world(src)] bumped per tile
+  uint32_t* peer_tile_counter[kMaxPeers];  // per-rank counter array [world(src)]
+};
+
+// C tensor maps: [0] = plain C; RS scatter: [d] = my slot in rank d's staging buffer
+struct GemmStoreMaps {
+  CUtensorMap m[kMaxPeers];
 };
 
 template <int BLOCK_N>
@@ -75,13 +84,14 @@ struct GemmSmem {
   static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStoreStageBytes = 2 * kStoreBytes;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+  static constexpr int kTotalBytes =
+      kStages * kStageBytes + kStoreStageBytes + kBarrierBytes + 1024 /*align slack*/;
 };
 
 // tile index -> (m_block, n_block) with grouped rasterisation so that concurrently running CTAs
-// share B tiles (and a few A tiles) in L2.  `m_shift` rotates the m order (used by the fused
-// collectives so that every rank starts on a different chunk).
+// share B tiles (and a few A tiles) in L2.
 TDP_DEVICE void tile_to_mn(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
   const int group = p.group_m;
   const int tiles_per_group = group * p.num_n_blocks;
@@ -107,10 +117,119 @@ TDP_DEVICE int remap_m_block(const GemmParams& p, int m_blk) {
   return chunk * blocks_per_chunk + r;
 }
 
+TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Everything between the accumulator and the store for one thread-row x 32 columns.
+// `full` = the 32 columns are all inside N.
+TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int col0, bool full) {
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (full || col0 + j + 8 <= p.N) {
+        const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
+        const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z),
+                     b3 = unpack_bf16x2(b.w);
+        v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b1.x; v[j + 3] += b1.y;
+        v[j + 4] += b2.x; v[j + 5] += b2.y; v[j + 6] += b3.x; v[j + 7] += b3.y;
+      }
+    }
+  }
+  if (p.aux_out != nullptr) {
+    __nv_bfloat16* arow = p.aux_out + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (full || col0 + j + 8 <= p.N) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(arow + j) = o;
+      }
+    }
+  }
+  if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  } else if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_DGELU_TANH || p.act == ACT_DGELU_ERF) {
+    const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (full || col0 + j + 8 <= p.N) {
+        const uint4 z = *reinterpret_cast<const uint4*>(zrow + j);
+        float zz[8];
+        float2 t;
+        t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
+        t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
+        t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
+        t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          v[j + q] *= (p.act == ACT_DGELU_TANH) ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
+      }
+    }
+  }
+  if (p.residual != nullptr) {
+    const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row) * p.ld_res + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (full || col0 + j + 8 <= p.N) {
+        const uint4 z = *reinterpret_cast<const uint4*>(rrow + j);
+        float2 t;
+        t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
+        t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
+        t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
+        t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
+      }
+    }
+  }
+}
+
+// direct (row-per-thread) global store, used for fp32 output / accumulate
+TDP_DEVICE void epilogue_store_direct(const GemmParams& p, float (&v)[32], uint8_t* c_row,
+                                      int col0, bool full) {
+  if (p.c_fp32) {
+    float* crow = reinterpret_cast<float*>(c_row) + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (full || col0 + j + 4 <= p.N) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(crow + j);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        *reinterpret_cast<float4*>(crow + j) = o;
+      }
+    }
+  } else {
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(c_row) + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (full || col0 + j + 8 <= p.N) {
+        if (p.accumulate) {
+          const uint4 z = *reinterpret_cast<const uint4*>(crow + j);
+          float2 t;
+          t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
+          t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
+          t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
+          t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(crow + j) = o;
+      }
+    }
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+                       const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ CUtensorMap tmap_a_local,
+                       const __grid_constant__ GemmStoreMaps store_maps, const GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (<= 512)
@@ -121,7 +240,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* smem_store = smem + kStages * S::kStageBytes;            // 2 x 16 KiB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + S::kStoreStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
@@ -160,17 +280,21 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int m_blk, n_blk;
         tile_to_mn(p, tile, m_blk, n_blk);
         m_blk = remap_m_block(p, m_blk);
+        int m0 = m_blk * kBlockM;
+        const CUtensorMap* amap = &tmap_a;
         if (p.comm_mode == COMM_AG_WAIT_A) {
-          const int chunk = (m_blk * kBlockM) / p.rows_per_chunk;
-          if (chunk != p.rank) {
+          const int chunk = m0 / p.rows_per_chunk;
+          if (chunk == p.rank && p.has_a_local) {
+            amap = &tmap_a_local;                 // zero-copy local shard, no wait
+            m0 -= chunk * p.rows_per_chunk;
+          } else {
             // wrap-safe "flag >= target" on monotonically increasing epochs
             while (static_cast<int32_t>(ld_acquire_sys(p.chunk_flags + chunk) - p.flag_target) < 0) {
             }
-            // peer / comm-CTA writes (generic proxy) -> our TMA reads (async proxy)
+            // peer / comm-kernel writes (generic proxy) -> our TMA reads (async proxy)
             fence_proxy_async_all();
           }
         }
-        const int m0 = m_blk * kBlockM;
         const int n0 = n_blk * BLOCK_N;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -179,11 +303,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint8_t* sb = smem_b + stage * S::kStageBytesB;
           const int k0 = kb * kBlockK;
           if (!p.a_mn_major) {
-            tma_load_2d(&tmap_a, &full_bar[stage], sa, k0, m0);
+            tma_load_2d(amap, &full_bar[stage], sa, k0, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (64 * kBlockK * 2), m0 + 64 * j, k0);
+              tma_load_2d(amap, &full_bar[stage], sa + j * (64 * kBlockK * 2), m0 + 64 * j, k0);
           }
           if (!p.b_mn_major) {
             tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);
@@ -247,164 +371,117 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // A warp may only touch TMEM lanes [32*(warp_idx%4), +32).
     const int quad = warp_idx & 3;
     const int lane = threadIdx.x & 31;
+    const bool issuer = (warp_idx == 2) && (lane == 0);   // the thread that owns the TMA stores
     int acc = 0;
     uint32_t acc_phase = 0;
+    int store_buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_to_mn(p, tile, m_blk, n_blk);
       m_blk = remap_m_block(p, m_blk);
-      const int row = m_blk * kBlockM + quad * 32 + lane;
+      const int row_in_tile = quad * 32 + lane;
+      const int row = m_blk * kBlockM + row_in_tile;
       const int n0 = n_blk * BLOCK_N;
       const bool row_ok = row < p.M;
-
-      // destination (plain: C ; RS scatter: owner's staging slot for our rank)
-      uint8_t* c_row;
-      int dst_rank = -1;
-      if (p.comm_mode == COMM_RS_SCATTER) {
-        dst_rank = (m_blk * kBlockM) / p.rows_per_chunk;
-        const int local_row = row - dst_rank * p.rows_per_chunk;
-        c_row = reinterpret_cast<uint8_t*>(p.peer_out[dst_rank]) +
-                (static_cast<size_t>(p.rank) * p.rows_per_chunk + local_row) *
-                    static_cast<size_t>(p.ldc) * 2;
-      } else {
-        c_row = reinterpret_cast<uint8_t*>(p.C) +
-                static_cast<size_t>(row) * p.ldc * (p.c_fp32 ? 4 : 2);
-      }
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
 
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row_ok && col0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          const bool full = (col0 + 32 <= p.N);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || col0 + j + 8 <= p.N) {
-                const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
-                const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y),
-                             b2 = unpack_bf16x2(b.z), b3 = unpack_bf16x2(b.w);
-                v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b1.x; v[j + 3] += b1.y;
-                v[j + 4] += b2.x; v[j + 5] += b2.y; v[j + 6] += b3.x; v[j + 7] += b3.y;
-              }
-            }
-          }
-          if (p.aux_out != nullptr) {
-            __nv_bfloat16* arow = p.aux_out + static_cast<size_t>(row) * p.ld_aux + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || col0 + j + 8 <= p.N) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(arow + j) = o;
-              }
-            }
-          }
-          if (p.act == ACT_GELU_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-          } else if (p.act == ACT_GELU_ERF) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == ACT_DGELU_TANH || p.act == ACT_DGELU_ERF) {
-            const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || col0 + j + 8 <= p.N) {
-                const uint4 z = *reinterpret_cast<const uint4*>(zrow + j);
-                float zz[8];
-                float2 t;
-                t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
-                t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
-                t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
-                t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  v[j + q] *= (p.act == ACT_DGELU_TANH) ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
-              }
-            }
-          }
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row) * p.ld_res + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || col0 + j + 8 <= p.N) {
-                const uint4 z = *reinterpret_cast<const uint4*>(rrow + j);
-                float2 t;
-                t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
-                t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
-                t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
-                t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
-              }
-            }
-          }
-          if (p.c_fp32) {
-            float* crow = reinterpret_cast<float*>(c_row) + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full || col0 + j + 4 <= p.N) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(crow + j);
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *reinterpret_cast<float4*>(crow + j) = o;
-              }
-            }
-          } else {
-            __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(c_row) + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || col0 + j + 8 <= p.N) {
-                if (p.accumulate) {
-                  const uint4 z = *reinterpret_cast<const uint4*>(crow + j);
-                  float2 t;
-                  t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
-                  t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
-                  t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
-                  t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
-                }
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                if (p.comm_mode == COMM_RS_SCATTER) st_na_v4(crow + j, o);   // peer store
-                else *reinterpret_cast<uint4*>(crow + j) = o;
-              }
-            }
-          }
+      if (p.use_tma_store) {
+        // ---- TMEM -> registers -> swizzled smem -> TMA store (128 rows x 64 cols at a time)
+        const CUtensorMap* cmap = &store_maps.m[0];
+        int dst_rank = -1;
+        int store_row0 = m_blk * kBlockM;
+        if (p.comm_mode == COMM_RS_SCATTER) {
+          dst_rank = store_row0 / p.rows_per_chunk;
+          cmap = &store_maps.m[dst_rank];
+          store_row0 -= dst_rank * p.rows_per_chunk;
         }
-      }
-      // accumulator drained: hand the TMEM stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-
-      if (p.comm_mode == COMM_RS_SCATTER) {
-        // publish this warp's quarter of the tile to the owner: all lanes' peer stores must be
-        // ordered before the counter bump (release at system scope).
-        __syncwarp();
-        if (lane == 0) {
+#pragma unroll 1
+        for (int sc = 0; sc < BLOCK_N; sc += kStoreCols) {
+          if (n0 + sc >= p.N) break;                          // warp-uniform
+          uint8_t* sbuf = smem_store + store_buf * kStoreBytes;
+          // the store issued two sub-tiles ago must have finished reading this buffer
+          if (issuer) tma_store_wait_read<1>();
+          epi_bar_sync();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + sc + h * 32, r);
+            tmem_ld_wait();
+            const int col0 = n0 + sc + h * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            if (row_ok && col0 < p.N) epilogue_math(p, v, row, col0, col0 + 32 <= p.N);
+            // row r of the staging tile: 128 bytes, 16-byte chunk c stored at (c ^ (r & 7))
+            uint8_t* srow = sbuf + row_in_tile * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              const int chunk = (h * 4 + j) ^ (row_in_tile & 7);
+              *reinterpret_cast<uint4*>(srow + chunk * 16) = o;
+            }
+          }
+          if (sc + kStoreCols >= BLOCK_N || n0 + sc + kStoreCols >= p.N) {
+            // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the TMA engine
+          epi_bar_sync();
+          if (issuer) {
+            tma_store_2d(cmap, sbuf, n0 + sc, store_row0);
+            tma_store_commit();
+          }
+          store_buf ^= 1;
+        }
+        if (p.comm_mode == COMM_RS_SCATTER && issuer) {
+          // all of this tile's bytes must have landed in the owner's memory before the counter
+          // moves: wait for full completion of the bulk stores, then release at system scope.
+          tma_store_wait<0>();
+          fence_proxy_async_all();
           fence_acq_rel_sys();
           // unit = (32 rows x 8 columns): independent of the tile shape chosen by the host
           red_add_release_sys(p.peer_tile_counter[dst_rank] + p.rank,
-                              static_cast<uint32_t>(min(BLOCK_N, p.N - n0) >> 3));
+                              static_cast<uint32_t>(4 * (min(BLOCK_N, p.N - n0) >> 3)));
         }
+      } else {
+        // ---- direct row-per-thread stores (fp32 output / accumulate)
+        uint8_t* c_row = reinterpret_cast<uint8_t*>(p.C) +
+                         static_cast<size_t>(row) * p.ldc * (p.c_fp32 ? 4 : 2);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c;
+          if (row_ok && col0 < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            const bool full = (col0 + 32 <= p.N);
+            epilogue_math(p, v, row, col0, full);
+            epilogue_store_direct(p, v, c_row, col0, full);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    // smem must stay valid until the last bulk stores have read it
+    if (issuer) tma_store_wait<0>();
   }
 
   tc_fence_before();

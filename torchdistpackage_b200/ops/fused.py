@@ -1,0 +1,288 @@
+"""Autograd / functional front-ends of the HBM-bound fused kernels (csrc/fused/*.cu) with
+PyTorch fallbacks for CPU tensors.
+
+    layer_norm(x, weight, bias, eps, residual=None) -> y  or (y, x + residual)
+    cross_entropy(logits, target, ignore_index)     -> mean loss  (fwd+bwd in ONE pass: the
+                                                       logits buffer is overwritten with dlogits)
+    FusedAdamW                                       flat multi-tensor AdamW driven by one launch
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from ._loader import native
+
+
+def _fused_ok(*ts) -> bool:
+    if native() is None:
+        return False
+    return all(t is None or (t.is_cuda and t.dtype == torch.bfloat16) for t in ts)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float, residual):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).contiguous()
+        r2 = residual.reshape(-1, shape[-1]).contiguous() if residual is not None else None
+        rows, cols = x2.shape
+        y = torch.empty_like(x2)
+        s = torch.empty_like(x2) if residual is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        native().layernorm_fwd(x2, r2, weight, bias, y, s, mean, rstd, float(eps))
+        ctx.save_for_backward(s if residual is not None else x2, weight, mean, rstd)
+        ctx.has_res, ctx.has_bias = residual is not None, bias is not None
+        ctx.shape = shape
+        if residual is not None:
+            return y.view(shape), s.view(shape)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy, ds=None):
+        xin, weight, mean, rstd = ctx.saved_tensors
+        rows, cols = xin.shape
+        dy2 = dy.reshape(rows, cols).contiguous()
+        ds2 = ds.reshape(rows, cols).contiguous() if (ctx.has_res and ds is not None) else None
+        dx = torch.empty_like(xin)
+        dgamma = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        dbeta = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        native().layernorm_bwd(dy2, xin, weight, mean, rstd, dx, ds2, dgamma, dbeta)
+        dxv = dx.view(ctx.shape)
+        return dxv, dgamma, (dbeta if ctx.has_bias else None), None, (dxv if ctx.has_res else None)
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+               eps: float = 1e-5, residual: Optional[torch.Tensor] = None):
+    """LayerNorm over the last dim.  With ``residual`` returns ``(LN(x + residual), x + residual)``
+    (the sum is produced by the same kernel: one read of each operand, two writes)."""
+    cols = x.shape[-1]
+    if _fused_ok(x, weight, bias, residual) and cols % 8 == 0 and cols <= 8192:
+        return _LayerNormFn.apply(x, weight, bias, eps, residual)
+    if residual is not None:
+        s = x + residual
+        return F.layer_norm(s, (cols,), weight, bias, eps), s
+    return F.layer_norm(x, (cols,), weight, bias, eps)
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """Mean cross entropy whose backward was already computed in forward (dlogits overwrite the
+    logits).  ``logits`` must therefore not be used afterwards -- it is the LM-head output."""
+
+    @staticmethod
+    def forward(ctx, logits2d, target, ignore_index: int):
+        rows = logits2d.shape[0]
+        n_valid = (target != ignore_index).sum().clamp_min(1)
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=logits2d.device)
+        # grad wrt the *mean*: scale by 1/n_valid; done on device without a sync by a second pass
+        native().cross_entropy_fwd_bwd(logits2d, target, loss_rows, 1.0, int(ignore_index))
+        inv = (1.0 / n_valid.float()).reshape(1)
+        ctx.save_for_backward(logits2d, inv)
+        return loss_rows.sum() * inv[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dlogits, inv = ctx.saved_tensors
+        coef = (dloss.float().reshape(1) * inv)
+        native().scale_(dlogits.view(-1) if dlogits.is_contiguous() else dlogits, 1.0, coef)
+        return dlogits, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = -100):
+    """Mean softmax cross entropy over ``[..., vocab]`` logits."""
+    vocab = logits.shape[-1]
+    l2 = logits.reshape(-1, vocab)
+    t = target.reshape(-1)
+    if _fused_ok(l2) and l2.is_contiguous() and logits.requires_grad and vocab % 8 == 0:
+        return _CrossEntropyFn.apply(l2, t.contiguous(), ignore_index)
+    return F.cross_entropy(l2.float(), t, ignore_index=ignore_index)
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW over *flat* buffers: every parameter (and its grad) of a group is a view into one
+    contiguous buffer, so ``step()`` is a single kernel launch per group
+    (csrc/fused/optim.cu ``adamw_kernel``) with fp32 master weights + moments and bf16 write-out.
+
+    Use :func:`flatten_module_params` (or NaiveDDP's bucket views for the grads) to obtain flat
+    storage; parameters that are not flat-backed fall back to per-tensor launches.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 master_weights: bool = True, adamw_mode: bool = True):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.master_weights = master_weights
+        self.adamw_mode = adamw_mode
+        self._flat = {}     # group index -> (flat_param, flat_grad or None)
+
+    def attach_flat(self, group_index: int, flat_param: torch.Tensor,
+                    flat_grad: Optional[torch.Tensor] = None) -> None:
+        """Declare that all params of ``group_index`` are views of ``flat_param`` (and their grads
+        views of ``flat_grad`` at the same offsets)."""
+        self._flat[group_index] = (flat_param, flat_grad)
+
+    def _state_for(self, key, like: torch.Tensor):
+        st = self.state[key]
+        if not st:
+            st["step"] = 0
+            st["exp_avg"] = torch.zeros(like.numel(), dtype=torch.float32, device=like.device)
+            st["exp_avg_sq"] = torch.zeros(like.numel(), dtype=torch.float32, device=like.device)
+            if self.master_weights and like.dtype != torch.float32:
+                st["master"] = like.detach().reshape(-1).float().clone()
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0, grad_scale_t: Optional[torch.Tensor] = None):
+        loss = closure() if closure is not None else None
+        C = native()
+        for gi, group in enumerate(self.param_groups):
+            b1, b2 = group["betas"]
+            flat = self._flat.get(gi)
+            if flat is not None and flat[1] is not None and C is not None and flat[0].is_cuda:
+                fp, fg = flat
+                st = self._state_for(group["params"][0], fp)
+                st["step"] += 1
+                C.adamw(fp, st.get("master"), fg, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1,
+                        b2, group["eps"], group["weight_decay"], st["step"], self.adamw_mode,
+                        grad_scale, grad_scale_t, None)
+                continue
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self._state_for(p, p)
+                st["step"] += 1
+                if C is not None and p.is_cuda and p.is_contiguous() and p.grad.is_contiguous() \
+                        and p.dtype in (torch.bfloat16, torch.float32):
+                    C.adamw(p.view(-1), st.get("master"), p.grad.view(-1), st["exp_avg"],
+                            st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                            group["weight_decay"], st["step"], self.adamw_mode, grad_scale,
+                            grad_scale_t, None)
+                else:
+                    g = p.grad.float().reshape(-1) * grad_scale
+                    w = st["master"] if "master" in st else p.data.float().reshape(-1)
+                    if self.adamw_mode:
+                        w.mul_(1 - group["lr"] * group["weight_decay"])
+                    else:
+                        g = g + group["weight_decay"] * w
+                    st["exp_avg"].mul_(b1).add_(g, alpha=1 - b1)
+                    st["exp_avg_sq"].mul_(b2).addcmul_(g, g, value=1 - b2)
+                    bc1 = 1 - b1 ** st["step"]
+                    bc2 = 1 - b2 ** st["step"]
+                    denom = (st["exp_avg_sq"].sqrt() / (bc2 ** 0.5)).add_(group["eps"])
+                    w.addcdiv_(st["exp_avg"], denom, value=-group["lr"] / bc1)
+                    p.data.copy_(w.view_as(p))
+        return loss
+
+
+class BucketAdamW:
+    """AdamW that runs once per :class:`NaiveDDP` gradient bucket.
+
+    NaiveDDP (``gradient_as_bucket_view=True``) keeps every gradient inside a few flat (symmetric
+    memory) buckets that the NVLS all-reduce kernel averages in place.  This optimizer mirrors
+    that layout for the parameters -- ``p.data`` becomes a view of a per-bucket flat parameter
+    buffer at the same offset as its gradient -- so the whole update of a bucket (fp32 master
+    weights + moments, bf16 write-out, optional clip coefficient) is ONE fused kernel launch that
+    can start as soon as that bucket's reduction has finished.  ``zero_grad`` is one memset per
+    bucket.  Exposes ``param_groups`` (one group) for LR schedulers.
+    """
+
+    def __init__(self, ddp, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 master_weights: bool = True, adamw_mode: bool = True):
+        red = ddp.reducer
+        if not red.as_view:
+            raise ValueError("BucketAdamW needs NaiveDDP(gradient_as_bucket_view=True)")
+        self.ddp = ddp
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                  params=[p for p in red.params.values() if p.requires_grad])]
+        self.adamw_mode = adamw_mode
+        self.step_count = 0
+        self.state = []
+        with torch.no_grad():
+            for b in red.buckets:
+                flat_p = torch.zeros(b.capacity, dtype=b.dtype, device=b.device)
+                esize = b.buffer.element_size()
+                for name in b.names:
+                    p = red.params[name]
+                    off = (b.views[name].data_ptr() - b.buffer.data_ptr()) // esize
+                    pv = flat_p[off:off + p.numel()].view(p.shape)
+                    pv.copy_(p.data)
+                    p.data = pv
+                st = dict(bucket=b, flat_p=flat_p,
+                          exp_avg=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
+                          exp_avg_sq=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
+                          master=(flat_p.float().clone() if master_weights and
+                                  b.dtype != torch.float32 else None))
+                self.state.append(st)
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0, grad_scale_t: Optional[torch.Tensor] = None):
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        self.step_count += 1
+        C = native()
+        for st in self.state:
+            fp, fg = st["flat_p"], st["bucket"].buffer[:st["bucket"].capacity]
+            if C is not None and fp.is_cuda and fp.dtype in (torch.bfloat16, torch.float32):
+                C.adamw(fp, st["master"], fg, st["exp_avg"], st["exp_avg_sq"], g["lr"], b1, b2,
+                        g["eps"], g["weight_decay"], self.step_count, self.adamw_mode, grad_scale,
+                        grad_scale_t, None)
+            else:
+                gr = fg.float() * grad_scale
+                if grad_scale_t is not None:
+                    gr = gr * grad_scale_t
+                w = st["master"] if st["master"] is not None else fp.float()
+                if self.adamw_mode:
+                    w.mul_(1 - g["lr"] * g["weight_decay"])
+                else:
+                    gr = gr + g["weight_decay"] * w
+                st["exp_avg"].mul_(b1).add_(gr, alpha=1 - b1)
+                st["exp_avg_sq"].mul_(b2).addcmul_(gr, gr, value=1 - b2)
+                bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
+                denom = (st["exp_avg_sq"].sqrt() / (bc2 ** 0.5)).add_(g["eps"])
+                w.addcdiv_(st["exp_avg"], denom, value=-g["lr"] / bc1)
+                fp.copy_(w)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        for st in self.state:
+            st["bucket"].buffer.zero_()
+
+    def state_dict(self) -> dict:
+        return dict(step=self.step_count, param_groups=[{k: v for k, v in g.items() if k != "params"}
+                                                        for g in self.param_groups],
+                    buckets=[dict(exp_avg=s["exp_avg"].cpu(), exp_avg_sq=s["exp_avg_sq"].cpu(),
+                                  master=None if s["master"] is None else s["master"].cpu())
+                             for s in self.state])
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        for g, sg in zip(self.param_groups, sd["param_groups"]):
+            g.update(sg)
+        for s, ss in zip(self.state, sd["buckets"]):
+            s["exp_avg"].copy_(ss["exp_avg"])
+            s["exp_avg_sq"].copy_(ss["exp_avg_sq"])
+            if s["master"] is not None and ss["master"] is not None:
+                s["master"].copy_(ss["master"])
+                s["flat_p"].copy_(s["master"])
+
+
+def flatten_module_params(module: torch.nn.Module, align_elems: int = 64):
+    """Re-home all parameters of ``module`` (single dtype) into one flat buffer.  Returns
+    ``flat_param``; each ``p.data`` becomes a view of it (registration order)."""
+    params = [p for p in module.parameters()]
+    assert params and all(p.dtype == params[0].dtype for p in params)
+    offs, total = [], 0
+    for p in params:
+        total = (total + align_elems - 1) // align_elems * align_elems
+        offs.append(total)
+        total += p.numel()
+    total = (total + align_elems - 1) // align_elems * align_elems
+    flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+    with torch.no_grad():
+        for p, o in zip(params, offs):
+            v = flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+    return flat, offs

@@ -1,0 +1,180 @@
+"""Autograd front-ends of the tcgen05 GEMM (csrc/gemm): linear / fused MLP with the elementwise
+work folded into the GEMM epilogues.
+
+    linear(x, w, bias, layout, act, residual)   y = act(x @ W + b) (+ residual)
+    mlp(x, w1, b1, w2, b2, ...)                 y = gelu(x @ W1 + b1) @ W2 + b2 (+ residual)
+
+``layout='kn'`` means ``w`` is ``[in, out]`` (the reference's TpLinear convention,
+tensor_parallel/tp_utils.py:162-174); ``layout='nk'`` is ``nn.Linear``'s ``[out, in]``.
+
+Backward uses the same kernel with the other operand majors (no transposes are materialised):
+dgrad = dy @ W^T, wgrad = x^T @ dy, and for the MLP the GELU derivative is applied in the epilogue
+of the fc2 dgrad GEMM (``ACT_DGELU``).  bf16 CUDA tensors take the native path; everything else
+(CPU, fp32) falls back to ``torch`` so the same modules run under gloo in the unit tests.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from ._loader import native
+
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_DGELU_TANH, ACT_DGELU_ERF = 0, 1, 2, 3, 4
+_ACT_CODE = {None: ACT_NONE, "none": ACT_NONE, "gelu_tanh": ACT_GELU_TANH, "gelu": ACT_GELU_ERF,
+             "gelu_erf": ACT_GELU_ERF}
+_DACT = {ACT_GELU_TANH: ACT_DGELU_TANH, ACT_GELU_ERF: ACT_DGELU_ERF}
+
+
+def _native_ok(*ts) -> bool:
+    if native() is None:
+        return False
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.bfloat16):
+            return False
+    return True
+
+
+def _as2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None, residual=None,
+         aux_in=None, aux_out=None, act=ACT_NONE, accumulate=False, alpha=1.0, block_n=0,
+         max_ctas=0):
+    """Raw kernel entry: ``out = act(alpha * op(a) @ op(b) + bias) (+ residual)``."""
+    M = a.shape[1] if trans_a else a.shape[0]
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype or torch.bfloat16, device=a.device)
+    native(required=True).gemm(a, b, out, trans_a, trans_b, bias, residual, aux_in, aux_out,
+                               int(act), bool(accumulate), float(alpha), int(block_n),
+                               int(max_ctas))
+    return out
+
+
+def colsum(x2d: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+    out = torch.empty(x2d.shape[1], dtype=out_dtype, device=x2d.device)
+    if x2d.shape[1] % 8 == 0 and x2d.stride(1) == 1:
+        native(required=True).colsum(x2d, out)
+    else:
+        out.copy_(x2d.float().sum(0))
+    return out
+
+
+def _act_ref(z, act):
+    if act == ACT_GELU_TANH:
+        return F.gelu(z, approximate="tanh")
+    if act == ACT_GELU_ERF:
+        return F.gelu(z)
+    return z
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, layout_nk: bool, act: int, residual):
+        x2 = _as2d(x)
+        N = w.shape[0] if layout_nk else w.shape[1]
+        need_z = act != ACT_NONE
+        z = torch.empty(x2.shape[0], N, dtype=torch.bfloat16, device=x.device) if need_z else None
+        res2 = _as2d(residual) if residual is not None else None
+        y = gemm(x2, w, trans_b=layout_nk, bias=bias, act=act, aux_out=z, residual=res2)
+        ctx.save_for_backward(x2, w, z)
+        ctx.layout_nk, ctx.act = layout_nk, act
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, z = ctx.saved_tensors
+        dy2 = _as2d(dy)
+        if ctx.act != ACT_NONE:
+            # dz = dy * act'(z): one elementwise pass folded into an identity-free path is not
+            # possible here (no GEMM precedes it), so use the GEMM-free torch ops
+            zf = z.float().requires_grad_(True)
+            with torch.enable_grad():
+                a = _act_ref(zf, ctx.act)
+            dz = torch.autograd.grad(a, zf, dy2.float())[0].to(torch.bfloat16)
+        else:
+            dz = dy2
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            # dx = dz @ W^T
+            dx = gemm(dz, w, trans_b=not ctx.layout_nk).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            if ctx.layout_nk:   # dW [N, K] = dz^T @ x
+                dw = gemm(dz, x2, trans_a=True)
+            else:               # dW [K, N] = x^T @ dz
+                dw = gemm(x2, dz, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dz)
+        if ctx.has_res and ctx.needs_input_grad[5]:
+            dres = dy
+        return dx, dw, db, None, None, dres
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           layout: str = "kn", act: Optional[str] = None,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    code = _ACT_CODE[act]
+    K = x.shape[-1]
+    N = w.shape[0] if layout == "nk" else w.shape[1]
+    if _native_ok(x, w, bias, residual) and K % 8 == 0 and N % 8 == 0:
+        return _LinearFn.apply(x, w, bias, layout == "nk", code, residual)
+    y = torch.matmul(x, w.t() if layout == "nk" else w)
+    if bias is not None:
+        y = y + bias
+    y = _act_ref(y, code)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+class _MlpFn(torch.autograd.Function):
+    """y = act(x W1 + b1) W2 + b2 (+ residual), all elementwise work in GEMM epilogues."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, layout_nk: bool, act: int, residual):
+        x2 = _as2d(x)
+        H = w1.shape[0] if layout_nk else w1.shape[1]
+        z = torch.empty(x2.shape[0], H, dtype=torch.bfloat16, device=x.device)
+        a = gemm(x2, w1, trans_b=layout_nk, bias=b1, act=act, aux_out=z)
+        res2 = _as2d(residual) if residual is not None else None
+        y = gemm(a, w2, trans_b=layout_nk, bias=b2, residual=res2)
+        ctx.save_for_backward(x2, w1, w2, z, a)
+        ctx.layout_nk, ctx.act = layout_nk, act
+        ctx.flags = (b1 is not None, b2 is not None, residual is not None)
+        ctx.x_shape = x.shape
+        N = w2.shape[0] if layout_nk else w2.shape[1]
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, w2, z, a = ctx.saved_tensors
+        nk = ctx.layout_nk
+        dy2 = _as2d(dy)
+        has_b1, has_b2, has_res = ctx.flags
+        # dz = (dy @ W2^T) * act'(z)   -- derivative applied in the epilogue
+        dz = gemm(dy2, w2, trans_b=not nk, act=_DACT[ctx.act], aux_in=z)
+        dw2 = gemm(dy2, a, trans_a=True) if nk else gemm(a, dy2, trans_a=True)
+        db2 = colsum(dy2) if has_b2 else None
+        dx = gemm(dz, w1, trans_b=not nk).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm(dz, x2, trans_a=True) if nk else gemm(x2, dz, trans_a=True)
+        db1 = colsum(dz) if has_b1 else None
+        dres = dy if has_res else None
+        return dx, dw1, db1, dw2, db2, None, None, dres
+
+
+def mlp(x, w1, b1, w2, b2, layout: str = "kn", act: str = "gelu",
+        residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    code = _ACT_CODE[act]
+    if _native_ok(x, w1, b1, w2, b2, residual) and code != ACT_NONE \
+            and all(d % 8 == 0 for d in (*w1.shape, *w2.shape)):
+        return _MlpFn.apply(x, w1, b1, w2, b2, layout == "nk", code, residual)
+    h = linear(x, w1, b1, layout, act)
+    return linear(h, w2, b2, layout, None, residual)
