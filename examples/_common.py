@@ -1,0 +1,19 @@
+import argparse, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torchdistpackage_b200 as tdp
+
+
+def init(desc=""):
+    ap = argparse.ArgumentParser(description=desc)
+    ap.add_argument("--cpu", action="store_true")
+    args, _ = ap.parse_known_args()
+    rank, world, _, _ = tdp.setup_distributed("gloo" if args.cpu or not torch.cuda.is_available() else "nccl")
+    dev = torch.device("cpu") if args.cpu or not torch.cuda.is_available() else \
+        torch.device("cuda", torch.cuda.current_device())
+    return rank, world, dev
+
+
+def log(rank, *a):
+    if rank == 0:
+        print(*a, flush=True)

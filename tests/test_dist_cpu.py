@@ -384,3 +384,48 @@ def _w_clip(rank, world):
 
 def test_clip_grad_norm_model_parallel():
     run_distributed(_w_clip, 4)
+
+
+# ------------------------------------------------------------------ MoE layer (expert parallel)
+def _w_moe_layer(rank, world):
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.moe import MoELayer
+    tdp.tpc.setup_process_groups([("data", world)])
+    tdp.tpc.build_moe_groups(moe_ep_size=2)
+    ep_group = tdp.tpc.get_group("moe_ep")
+    ep_rank = tdp.tpc.get_group_rank("moe_ep")
+    dim, hid, E = 16, 32, 4
+    torch.manual_seed(0)
+    serial = MoELayer(dim, hid, num_experts=E, top_k=2, capacity_factor=8.0, expert_parallel=False)
+    par = MoELayer(dim, hid, num_experts=E, top_k=2, capacity_factor=8.0, ep_group=ep_group)
+    with torch.no_grad():
+        par.gate.wg.copy_(serial.gate.wg)
+        el = E // 2
+        for name in ("w1", "b1", "w2", "b2"):
+            getattr(par.experts, name).copy_(getattr(serial.experts, name)[ep_rank * el:(ep_rank + 1) * el])
+    torch.manual_seed(100 + ep_rank)
+    x = torch.randn(12, dim, requires_grad=True)
+    y, aux = par(x)
+    (y.pow(2).sum() + aux).backward()
+    xs = x.detach().clone().requires_grad_(True)
+    ys, auxs = serial(xs)
+    (ys.pow(2).sum() + auxs).backward()
+    assert torch.allclose(y, ys, atol=1e-5)
+    assert torch.allclose(x.grad, xs.grad, atol=1e-4)
+    # expert grads: my local experts see tokens from both EP ranks; compare against the serial
+    # layer fed with the concatenation of both ranks' tokens
+    xs_all = []
+    for r in range(2):
+        torch.manual_seed(100 + r)
+        xs_all.append(torch.randn(12, dim))
+    serial.zero_grad()
+    tot = 0
+    for xa in xs_all:
+        ya, aa = serial(xa)
+        tot = tot + ya.pow(2).sum() + aa
+    tot.backward()
+    assert torch.allclose(par.experts.w1.grad, serial.experts.w1.grad[ep_rank * el:(ep_rank + 1) * el], atol=1e-4)
+
+
+def test_moe_layer_expert_parallel_matches_serial():
+    run_distributed(_w_moe_layer, 2)
