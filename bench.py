@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--model", default="small", choices=["small", "medium", "tiny"])
     ap.add_argument("--micro-batch", type=int, default=MICRO_BATCH)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="ours: run the step eagerly")
     return ap.parse_args()
 
 
@@ -123,7 +124,7 @@ def build_ours(args, device, world):
     opt = BucketAdamW(ddp, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
     native = tdp.ops.native()
 
-    def step(tokens, targets):
+    def eager_step(tokens, targets):
         opt.zero_grad()
         loss = ddp(tokens, targets)
         loss.backward()
@@ -131,10 +132,33 @@ def build_ours(args, device, world):
         opt.step()
         return loss
 
-    def launches():
-        return int(native.launch_count()) if native is not None else 0
+    state = {"graph": None, "launches_per_replay": 0}
 
-    return step, launches, model.cfg
+    def step(tokens, targets):
+        """Public training step: the eager step captured once into a CUDA graph, then replayed."""
+        if args.no_graph:
+            return eager_step(tokens, targets)
+        if state["graph"] is None:
+            from torchdistpackage_b200.ops.graph import GraphedStep
+            before = int(native.launch_count())
+            state["graph"] = GraphedStep(eager_step, (tokens, targets), warmup=2)
+            # kernels of ours inside one captured step (warm-up iterations + capture = 3 steps)
+            state["launches_per_replay"] = (int(native.launch_count()) - before) // 3
+        return state["graph"](tokens, targets)
+
+    replays = {"n": 0}
+
+    def counted_step(tokens, targets):
+        replays["n"] += 1
+        return step(tokens, targets)
+
+    def launches():
+        if args.no_graph:
+            return int(native.launch_count()) if native is not None else 0
+        # a replay re-launches every captured kernel; the host-side counter does not see replays
+        return replays["n"] * state["launches_per_replay"]
+
+    return counted_step, launches, model.cfg
 
 
 def main():
@@ -165,16 +189,19 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     import torch.distributed as dist
-    if world > 1:
-        if args.impl == "reference":
-            ref_bench.init_distributed()
-        else:
-            import torchdistpackage_b200 as tdp
-            tdp.setup_distributed("nccl")
-    assert world == args.gpus or world == 1 and args.gpus == 1, \
-        f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
-
-    step, launches, cfg = builder(args, device, world)
+    import contextlib
+    # stdout carries exactly ONE JSON line: library chatter (the reference prints from
+    # setup_distributed / group creation) goes to stderr
+    with contextlib.redirect_stdout(sys.stderr):
+        if world > 1:
+            if args.impl == "reference":
+                ref_bench.init_distributed()
+            else:
+                import torchdistpackage_b200 as tdp
+                tdp.setup_distributed("nccl")
+        assert world == args.gpus or world == 1 and args.gpus == 1, \
+            f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+        step, launches, cfg = builder(args, device, world)
     B, S = args.micro_batch, cfg.seq_len
     K, W = args.steps, args.warmup
     gen = torch.Generator().manual_seed(1234 + rank)

@@ -1,0 +1,164 @@
+"""N-GPU check of the engines on their native (symmetric-memory) paths:
+NaiveDDP (NVLS buckets) vs NCCL-averaged grads, BucketAdamW, Bf16ZeroOptimizer (RS -> fused Adam ->
+AG) vs torch AdamW on the full model, ShardedEMA multi-tensor kernel, MoE layer with P2P
+dispatch/combine vs its all_to_all fallback, PP 1F1B on NCCL p2p."""
+import copy, json, os, sys
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torchdistpackage_b200 as tdp
+from torchdistpackage_b200.models.gpt2 import build_gpt2
+from torchdistpackage_b200.ops.fused import BucketAdamW
+
+rank, world, _, _ = tdp.setup_distributed("nccl")
+tdp.tpc.verbose = False
+dev = torch.device("cuda", torch.cuda.current_device())
+res, ok = {"world": world}, True
+def log(*a):
+    if rank == 0: print(*a, flush=True)
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+def check(name, val, tol):
+    global ok
+    good = val < tol
+    ok &= good
+    res[name] = val
+    log(f"{name}: {val:.3e} {'OK' if good else 'FAIL'}")
+
+tdp.tpc.setup_process_groups([("data", world)])
+dp = tdp.tpc.get_group("data")
+
+# ---------------------------------------------------------------- NaiveDDP on symmetric buckets
+tdp.fix_rand(0, deterministic_cudnn=False)
+model = build_gpt2("tiny", device=dev)
+ref = copy.deepcopy(model)
+ddp = tdp.NaiveDDP(model, gradient_as_bucket_view=True, process_group=dp, bucket_cap_mb=0.25)
+res["ddp_symm_buckets"] = sum(b.symm is not None for b in ddp.buckets)
+log("DDP buckets:", len(ddp.buckets), "symmetric:", res["ddp_symm_buckets"])
+ok &= res["ddp_symm_buckets"] == len(ddp.buckets)
+torch.manual_seed(100 + rank)
+tok = torch.randint(0, model.cfg.vocab_size, (4, model.cfg.seq_len + 1), device=dev)
+for it in range(2):
+    for p in model.parameters():
+        if p.grad is not None: p.grad.zero_()
+    loss = ddp(tok[:, :-1], tok[:, 1:]); loss.backward(); ddp.reduce_gradients()
+ref(tok[:, :-1], tok[:, 1:]).backward()
+worst = 0.0
+for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+    g = q.grad.float().clone(); dist.all_reduce(g); g /= world
+    worst = max(worst, rel(p.grad, g))
+check("ddp_grad_vs_nccl_avg", worst, 3e-2)
+
+# BucketAdamW vs torch AdamW (fp32 master) for 3 steps on the averaged grads
+opt = BucketAdamW(ddp, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+ref32 = copy.deepcopy(ref).float()
+ropt = torch.optim.AdamW(ref32.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+with torch.no_grad():
+    for p, q in zip(ref32.parameters(), model.parameters()):
+        p.copy_(q.float())
+for it in range(3):
+    opt.zero_grad()
+    ddp(tok[:, :-1], tok[:, 1:]).backward(); ddp.reduce_gradients()
+    for p, q in zip(ref32.parameters(), model.parameters()):
+        p.grad = q.grad.float().clone()
+    opt.step(); ropt.step()
+worst = max(rel(q, p) for p, q in zip(ref32.parameters(), model.parameters()))
+check("bucket_adamw_vs_torch", worst, 2e-2)
+del ddp, opt
+
+# ---------------------------------------------------------------- ZeRO (bf16 model, fused path)
+tdp.fix_rand(1, deterministic_cudnn=False)
+zm = nn.Sequential(nn.Linear(256, 1024), nn.GELU(), nn.Linear(1024, 512), nn.GELU(), nn.Linear(512, 64)).to(dev).to(torch.bfloat16)
+zref = copy.deepcopy(zm).float()
+zropt = torch.optim.AdamW(zref.parameters(), lr=1e-3, weight_decay=0.01)
+zopt = tdp.Bf16ZeroOptimizer(torch.optim.AdamW(zm.parameters(), lr=1e-3, weight_decay=0.01),
+                             dp_group=dp, overlap_comm=True, bucket_size=300_000)
+res["zero_symm"] = all(s is not None for s in zopt.symm)
+res["zero_fused_adam"] = zopt._fused_adam_ok(0)
+log("ZeRO symmetric:", res["zero_symm"], "fused adam:", res["zero_fused_adam"], "buckets:", len(zopt.buckets))
+ok &= res["zero_symm"] and res["zero_fused_adam"]
+for it in range(4):
+    xs = []
+    for r in range(world):
+        torch.manual_seed(1000 * it + r)
+        xs.append(torch.randn(64, 256, device=dev))
+    zopt.zero_grad()
+    zm(xs[rank].to(torch.bfloat16)).float().pow(2).mean().backward()
+    zopt.step()
+    zropt.zero_grad()
+    (sum(zref(x.to(torch.bfloat16).float()).pow(2).mean() for x in xs) / world).backward()
+    zropt.step()
+check("zero_params_vs_torch_adamw", max(rel(p, q) for p, q in zip(zm.parameters(), zref.parameters())), 3e-2)
+sd = zopt.state_dict(); zopt.load_state_dict(sd)
+del zopt
+
+# ---------------------------------------------------------------- ShardedEMA multi-tensor kernel
+em = nn.Sequential(*[nn.Linear(128, 128) for _ in range(6)]).to(dev).to(torch.bfloat16)
+ema = tdp.ShardedEMA(em, group=dp)
+full = {n: p.detach().clone().float() for n, p in em.named_parameters()}
+for it in range(10):
+    with torch.no_grad():
+        for p in em.parameters(): p.add_(torch.randn_like(p) * 0.1)
+    ema.update(em, decay=0.9)
+    for n, p in em.named_parameters(): full[n].mul_(0.9).add_(p.detach().float(), alpha=0.1)
+check("sharded_ema_vs_full", max(rel(t, full[n]) for n, t in ema.state_dict_shard().items()), 3e-2)
+sdc = ema.state_dict_cpu()
+ok &= (sdc is not None) == (rank == 0)
+
+# ---------------------------------------------------------------- MoE: P2P kernels vs fallback
+if world % 2 == 0:
+    from torchdistpackage_b200.moe import MoELayer
+    from torchdistpackage_b200.moe import layer as moe_layer
+    tdp.tpc.build_moe_groups(moe_ep_size=2)
+    epg = tdp.tpc.get_group("moe_ep")
+    tdp.fix_rand(5, deterministic_cudnn=False)
+    moe = MoELayer(256, 512, num_experts=4, top_k=2, capacity_factor=4.0, ep_group=epg).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        dist.broadcast(moe.gate.wg.data, tdp.tpc.get_ranks_in_group("moe_ep")[0], group=epg)
+    torch.manual_seed(300 + rank)
+    x = torch.randn(512, 256, device=dev).to(torch.bfloat16).requires_grad_(True)
+    y, aux = moe(x); (y.float().pow(2).mean() + aux).backward()
+    res["moe_symm"] = moe._a2a.sym is not None
+    gx, gw = x.grad.clone(), moe.experts.w1.grad.clone()
+    # same layer through the all_to_all fallback
+    moe._a2a.sym = None
+    x2 = x.detach().clone().requires_grad_(True)
+    moe.zero_grad()
+    y2, aux2 = moe(x2); (y2.float().pow(2).mean() + aux2).backward()
+    check("moe_fwd_p2p_vs_a2a", rel(y, y2), 2e-2)
+    check("moe_dx_p2p_vs_a2a", rel(gx, x2.grad), 3e-2)
+    check("moe_dw_p2p_vs_a2a", rel(gw, moe.experts.w1.grad), 3e-2)
+    ok &= res["moe_symm"]
+
+# ---------------------------------------------------------------- pipeline 1F1B over NCCL p2p
+if world >= 2:
+    from torchdistpackage_b200.parallel import forward_backward, partition_uniform
+    tdp.tpc.reset(); tdp.tpc.verbose = False
+    tdp.tpc.setup_process_groups([("data", world // 2), ("pipe", 2)])
+    tdp.fix_rand(0, deterministic_cudnn=False)
+    layers = [nn.Linear(64, 64) for _ in range(4)]
+    full_model = nn.Sequential(*copy.deepcopy(layers)).to(dev)
+    stage = nn.Sequential(*partition_uniform(layers)).to(dev)
+    first, last = tdp.tpc.is_first_in_pipeline_group(), tdp.tpc.is_last_in_pipeline_group()
+    torch.manual_seed(9 + tdp.tpc.get_dp_rank())
+    xb, yb = torch.randn(16, 64, device=dev), torch.randn(16, 64, device=dev)
+    def fwd(inp):
+        if last:
+            act, tgt = inp
+            return (stage(act) - tgt).pow(2).sum() / 16
+        return stage(inp)
+    forward_backward(None, fwd, None, ([xb] if first else []) + ([yb] if last else []),
+                     num_microbatches=4, dtype=torch.float32)
+    ((full_model(xb) - yb).pow(2).sum() / 16).backward()
+    beg = tdp.tpc.get_pp_rank() * 2
+    torch.cuda.synchronize()
+    check("pp_1f1b_grads", max(rel(stage[i].weight.grad, full_model[beg + i].weight.grad) for i in range(2)), 1e-3)
+
+res["all_ok"] = bool(ok)
+flag = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open(f"gpurun_out/engines_check_w{world}.json", "w"), indent=1)
+    print("ALL_OK", bool(flag.item()), flush=True)
+dist.barrier(); dist.destroy_process_group()

@@ -34,15 +34,21 @@ struct PeerPtrs {
 
 __device__ __forceinline__ void put_signal(uint32_t* addr) {
   uint32_t old;
-  do {
+  SpinWatchdog wd;
+  for (;;) {
     asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
-  } while (old != 0u);
+    if (old == 0u) break;
+    wd.tick("barrier put_signal", threadIdx.x, 0);
+  }
 }
 __device__ __forceinline__ void wait_signal(uint32_t* addr) {
   uint32_t old;
-  do {
+  SpinWatchdog wd;
+  for (;;) {
     asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
-  } while (old != 1u);
+    if (old == 1u) break;
+    wd.tick("barrier wait_signal", threadIdx.x, 1);
+  }
 }
 
 // Block-level barrier with the same-index block of every peer.  Slot layout (uint32 words):
@@ -310,7 +316,9 @@ rs_reduce_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int wo
   // wait until every source rank has delivered all of its tiles for my chunk
   if (threadIdx.x < world) {
     const uint32_t* cnt = pp.signal[rank] + r.counter_word_offset + threadIdx.x;
+    SpinWatchdog wd;
     while (static_cast<int32_t>(ld_acquire_sys(cnt) - r.counter_target) < 0) {
+      wd.tick("reduce-scatter tile counter (rs_reduce)", threadIdx.x, rank);
     }
   }
   __syncthreads();

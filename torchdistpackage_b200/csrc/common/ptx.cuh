@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tdp {
 
@@ -42,6 +43,25 @@ TDP_DEVICE uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// Watchdog for cross-GPU spin waits: a peer that never arrives must become an error
+// (cudaErrorLaunchFailure on this rank) instead of a hung box.  ~10 s.
+constexpr uint64_t kSpinTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;
+struct SpinWatchdog {
+  uint64_t t0;
+  uint32_t polls;
+  TDP_DEVICE SpinWatchdog() : t0(0), polls(0) {}
+  // call once per failed poll; `what` / a / b are printed when the wait times out
+  TDP_DEVICE void tick(const char* what, int a, int b) {
+    if ((++polls & 0x3FFu) != 0u) return;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; return; }
+    if (now - t0 > kSpinTimeoutNs) {
+      printf("[tdp] spin wait timed out: %s (%d, %d) block %d\n", what, a, b, blockIdx.x);
+      __trap();
+    }
+  }
+};
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier
@@ -79,7 +99,9 @@ TDP_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 TDP_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  SpinWatchdog wd;
   while (!mbar_try_wait(bar, parity)) {
+    wd.tick("mbarrier", static_cast<int>(smem_u32(bar)), static_cast<int>(parity));
   }
 }
 

@@ -123,6 +123,7 @@ struct AdamWLaunch {
   const float* grad_scale_ptr;  // optional device scalar multiplied in as well
   void* param_copy_out;    // optional second bf16 destination (e.g. symmetric all-gather slot)
   int adamw_mode;          // 1: decoupled weight decay (AdamW), 0: L2 added to the gradient (Adam)
+  const float* hyper;      // optional device floats {step, lr}: overrides lr / bias corrections
 };
 void launch_adamw(const AdamWLaunch& a, cudaStream_t stream);
 

@@ -75,8 +75,15 @@ __global__ void __launch_bounds__(kThreads)
 adamw_kernel(void* __restrict__ param, float* __restrict__ master, const void* __restrict__ grad,
              float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, size_t numel,
              AdamConsts c, const float* __restrict__ gscale_ptr, void* __restrict__ copy_out,
-             int aligned) {
+             int aligned, const float* __restrict__ hyper) {
   if (gscale_ptr) c.gscale *= *gscale_ptr;
+  if (hyper) {
+    // device-resident step / lr (CUDA-graph replay: the host values are frozen at capture time)
+    const float step = hyper[0];
+    c.lr = hyper[1];
+    c.bc1 = 1.f - powf(c.beta1, step);
+    c.bc2_sqrt = sqrtf(1.f - powf(c.beta2, step));
+  }
   const size_t n4 = aligned ? numel / 4 : 0;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -232,7 +239,7 @@ void launch_adamw(const AdamWLaunch& a, cudaStream_t stream) {
   const int aligned = (bits & 15) == 0;
 #define TDP_ADAM(PB, GB, HM)                                                              \
   adamw_kernel<PB, GB, HM><<<grid, kThreads, 0, stream>>>(a.param, a.master, a.grad,      \
-      a.exp_avg, a.exp_avg_sq, a.numel, c, a.grad_scale_ptr, a.param_copy_out, aligned)
+      a.exp_avg, a.exp_avg_sq, a.numel, c, a.grad_scale_ptr, a.param_copy_out, aligned, a.hyper)
   const bool hm = a.master != nullptr;
   if (a.param_bf16 && a.grad_bf16) { if (hm) TDP_ADAM(true, true, true); else TDP_ADAM(true, true, false); }
   else if (a.param_bf16 && !a.grad_bf16) { if (hm) TDP_ADAM(true, false, true); else TDP_ADAM(true, false, false); }

@@ -71,7 +71,10 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     // worker threads (autograd engine) may not have a current context yet: bind it and retry
-    cudaFree(nullptr);
+    // (cudaSetDevice is legal during stream capture, cudaFree would not be)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(dev);
     r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -85,9 +85,11 @@ struct GemmSmem {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kStoreStageBytes = 2 * kStoreBytes;
-  static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotalBytes =
-      kStages * kStageBytes + kStoreStageBytes + kBarrierBytes + 1024 /*align slack*/;
+  static constexpr int kBarrierBytes = 256;
+  // 229 632 B: leaves > 2 KiB of the SM's 228 KiB so that a small communication CTA (push /
+  // all-reduce kernels, no dynamic smem) can always be co-resident with a persistent GEMM CTA --
+  // the fused all-gather->GEMM must never be able to starve the kernel it is waiting for.
+  static constexpr int kTotalBytes = kStages * kStageBytes + kStoreStageBytes + kBarrierBytes;
 };
 
 // tile index -> (m_block, n_block) with grouped rasterisation so that concurrently running CTAs
@@ -235,9 +237,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (<= 512)
   static_assert(kTmemCols <= 512, "TMEM overflow");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B swizzle needs 1 KiB alignment
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kStageBytesA;
   uint8_t* smem_store = smem + kStages * S::kStageBytes;            // 2 x 16 KiB, 1024-aligned
@@ -289,7 +291,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
             m0 -= chunk * p.rows_per_chunk;
           } else {
             // wrap-safe "flag >= target" on monotonically increasing epochs
+            SpinWatchdog wd;
             while (static_cast<int32_t>(ld_acquire_sys(p.chunk_flags + chunk) - p.flag_target) < 0) {
+              wd.tick("all-gather chunk flag (gemm producer)", chunk, p.rank);
             }
             // peer / comm-kernel writes (generic proxy) -> our TMA reads (async proxy)
             fence_proxy_async_all();

@@ -273,6 +273,7 @@ class _GradReducer:
         if self.on_cuda:
             cur = torch.cuda.current_stream(self.device)
             self.comm_stream.wait_stream(cur)       # device-side dependency only
+            self._comm_used = True
             with torch.cuda.stream(self.comm_stream):
                 self._pack(bucket)
                 payload = bucket.payload()
@@ -302,7 +303,11 @@ class _GradReducer:
                     pass
                 self._reduce_bucket(bucket)
         if self.on_cuda:
-            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            # (only when something was enqueued: waiting on an idle, non-capturing stream would be
+            # an illegal cross-capture dependency under CUDA-graph capture)
+            if getattr(self, "_comm_used", False):
+                torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+                self._comm_used = False
         else:
             for bucket in self.buckets:
                 if bucket.pending_work is not None:

@@ -200,6 +200,13 @@ class BucketAdamW:
         self.adamw_mode = adamw_mode
         self.step_count = 0
         self.state = []
+        # device-resident {step, lr}: the kernel derives the bias corrections from it, so a
+        # CUDA-graph replay of step() keeps advancing (host scalars are frozen at capture time)
+        self._hyper = None
+        self._hyper_lr = None
+        if red.on_cuda:
+            self._hyper = torch.tensor([0.0, float(lr)], dtype=torch.float32, device=red.device)
+            self._hyper_lr = float(lr)
         with torch.no_grad():
             for b in red.buckets:
                 flat_p = torch.zeros(b.capacity, dtype=b.dtype, device=b.device)
@@ -223,12 +230,17 @@ class BucketAdamW:
         b1, b2 = g["betas"]
         self.step_count += 1
         C = native()
+        if self._hyper is not None:
+            if not torch.cuda.is_current_stream_capturing() and g["lr"] != self._hyper_lr:
+                self._hyper[1].fill_(float(g["lr"]))      # LR schedulers edit param_groups
+                self._hyper_lr = float(g["lr"])
+            self._hyper[0:1].add_(1.0)                    # captured: advances on every replay
         for st in self.state:
             fp, fg = st["flat_p"], st["bucket"].buffer[:st["bucket"].capacity]
             if C is not None and fp.is_cuda and fp.dtype in (torch.bfloat16, torch.float32):
                 C.adamw(fp, st["master"], fg, st["exp_avg"], st["exp_avg_sq"], g["lr"], b1, b2,
                         g["eps"], g["weight_decay"], self.step_count, self.adamw_mode, grad_scale,
-                        grad_scale_t, None)
+                        grad_scale_t, None, self._hyper)
             else:
                 gr = fg.float() * grad_scale
                 if grad_scale_t is not None:
