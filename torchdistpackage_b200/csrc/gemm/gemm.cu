@@ -238,7 +238,24 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     p.use_tma_store = 1;
   }
 
-  const long tiles = static_cast<long>(p.num_m_blocks) * p.num_n_blocks;
+  // split-K (weight-gradient shapes: few output tiles, very long K): partials are added with
+  // vector atomics into an fp32 output that the caller zero-initialised (or accumulates into)
+  p.split_k = 1;
+  p.k_blocks_per_split = p.num_k_blocks;
+  if (g.split_k > 1) {
+    if (!g.c_fp32 || g.comm_mode != 0 || g.bias || g.residual || g.aux_in || g.aux_out ||
+        g.act != 0) {
+      snprintf(msg, sizeof(msg), "gemm: split_k needs a plain fp32 output (no fused epilogue)");
+      return -1;
+    }
+    int s = g.split_k < p.num_k_blocks ? g.split_k : p.num_k_blocks;
+    const int kpb = (p.num_k_blocks + s - 1) / s;
+    p.k_blocks_per_split = kpb;
+    p.split_k = (p.num_k_blocks + kpb - 1) / kpb;     // no empty splits
+    p.use_tma_store = 0;
+  }
+
+  const long tiles = static_cast<long>(p.num_m_blocks) * p.num_n_blocks * p.split_k;
   const int grid = static_cast<int>(tiles < max_ctas ? tiles : max_ctas);
   cudaError_t e = (block_n == 256) ? launch_impl<256>(ta, tb, ta_local, sm, p, grid, stream)
                                    : launch_impl<128>(ta, tb, ta_local, sm, p, grid, stream);

@@ -63,6 +63,8 @@ struct GemmParams {
   int ld_aux;
   int act;
   int group_m;                    // rasterisation group
+  int split_k;                    // >1: K is split over CTAs, partials atomically added (fp32 C)
+  int k_blocks_per_split;
   // ---- fused collective hooks ----
   int comm_mode;
   int rank, world;
@@ -193,6 +195,17 @@ TDP_DEVICE void epilogue_store_direct(const GemmParams& p, float (&v)[32], uint8
                                       int col0, bool full) {
   if (p.c_fp32) {
     float* crow = reinterpret_cast<float*>(c_row) + col0;
+    if (p.split_k > 1) {
+      // split-K partial: vector atomic add into the (pre-zeroed / accumulating) fp32 output
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (full || col0 + j + 4 <= p.N)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v[j]),
+                       "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (full || col0 + j + 4 <= p.N) {
@@ -251,7 +264,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp_idx = threadIdx.x / 32;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;   // work items
 
   if (warp_idx == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -280,7 +293,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_to_mn(p, tile, m_blk, n_blk);
+        tile_to_mn(p, tile / p.split_k, m_blk, n_blk);
+        const int kb0 = (tile % p.split_k) * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
         m_blk = remap_m_block(p, m_blk);
         int m0 = m_blk * kBlockM;
         const CUtensorMap* amap = &tmap_a;
@@ -300,7 +315,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         const int n0 = n_blk * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
           uint8_t* sa = smem_a + stage * S::kStageBytesA;
@@ -344,7 +359,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int kb0 = (tile % p.split_k) * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -354,10 +371,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = make_umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_f16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                 // frees the smem slot when MMAs finish
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator ready
+          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator ready
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -381,7 +398,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int store_buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_to_mn(p, tile, m_blk, n_blk);
+      tile_to_mn(p, tile / p.split_k, m_blk, n_blk);
       m_blk = remap_m_block(p, m_blk);
       const int row_in_tile = quad * 32 + lane;
       const int row = m_blk * kBlockM + row_in_tile;

@@ -120,10 +120,10 @@ class GPT2(nn.Module):
 
     def head_loss(self, x: torch.Tensor, targets: Optional[torch.Tensor]):
         x = F_ops.layer_norm(x, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps)
-        logits = L_ops.linear(x, self.wte.weight, None, layout="nk")       # tied embedding
         if targets is None:
-            return logits
-        return F_ops.cross_entropy(logits, targets)
+            return L_ops.linear(x, self.wte.weight, None, layout="nk")     # tied embedding
+        # LM head + CE + both LM-head backward GEMMs fused into one terminal op
+        return F_ops.lm_head_loss(x, self.wte.weight, targets)
 
     def forward(self, idx: torch.Tensor, targets: Optional[torch.Tensor] = None):
         x = self.embed(idx)

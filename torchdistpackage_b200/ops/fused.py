@@ -101,6 +101,58 @@ def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int 
     return F.cross_entropy(l2.float(), t, ignore_index=ignore_index)
 
 
+class _LmHeadLossFn(torch.autograd.Function):
+    """LM head + softmax cross entropy as ONE terminal op: logits = h @ W^T (tcgen05 GEMM), fused
+    CE kernel overwrites them with d(logits) (already scaled by 1/num_valid), and the two
+    backward GEMMs (d_h = dlogits @ W, d_W = dlogits^T @ h) run right away while the logits are
+    hot -- the [tokens, vocab] tensor never outlives forward and is touched 3 times instead of 6.
+    Backward only rescales the two small gradients by the incoming d(loss)."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, target, ignore_index: int, num_valid: int):
+        from . import linear as L
+        C = native()
+        D = hidden.shape[-1]
+        h2 = hidden.reshape(-1, D)
+        h2 = h2 if h2.is_contiguous() else h2.contiguous()
+        logits = L.gemm(h2, weight, trans_b=True)                       # [T, V]
+        loss_rows = torch.empty(h2.shape[0], dtype=torch.float32, device=h2.device)
+        C.cross_entropy_fwd_bwd(logits, target.reshape(-1).contiguous(), loss_rows,
+                                1.0 / float(num_valid), int(ignore_index))
+        d_h = L.gemm(logits, weight)                                    # [T, D]
+        d_w = L.gemm(logits, h2, trans_a=True)                          # [V, D]
+        ctx.save_for_backward(d_h, d_w)
+        ctx.h_shape = hidden.shape
+        return loss_rows.sum() / float(num_valid)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        d_h, d_w = ctx.saved_tensors
+        C = native()
+        s = dloss.reshape(1).float()
+        C.scale_(d_h.view(-1), 1.0, s)
+        C.scale_(d_w.view(-1), 1.0, s)
+        return d_h.view(ctx.h_shape), d_w, None, None, None
+
+
+def lm_head_loss(hidden: torch.Tensor, weight: torch.Tensor, target: torch.Tensor,
+                 ignore_index: Optional[int] = None) -> torch.Tensor:
+    """Mean next-token cross entropy of ``hidden @ weight^T`` (``weight`` = tied embedding
+    ``[vocab, dim]``).  ``ignore_index=None`` means every target counts (no host sync); with an
+    ignore index the number of valid targets is read back once."""
+    V, D = weight.shape
+    if _fused_ok(hidden, weight) and V % 8 == 0 and D % 8 == 0 and hidden.requires_grad:
+        if ignore_index is None:
+            n_valid, ign = target.numel(), -100
+            # (-100 never occurs in token ids, so nothing is ignored)
+        else:
+            n_valid, ign = int((target != ignore_index).sum().item()), int(ignore_index)
+        return _LmHeadLossFn.apply(hidden, weight, target, ign, max(n_valid, 1))
+    logits = torch.matmul(hidden, weight.t())
+    return F.cross_entropy(logits.reshape(-1, V).float(), target.reshape(-1),
+                           ignore_index=-100 if ignore_index is None else ignore_index)
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """AdamW over *flat* buffers: every parameter (and its grad) of a group is a view into one
     contiguous buffer, so ``step()`` is a single kernel launch per group

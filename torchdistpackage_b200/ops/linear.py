@@ -45,16 +45,45 @@ def _as2d(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None, residual=None,
          aux_in=None, aux_out=None, act=ACT_NONE, accumulate=False, alpha=1.0, block_n=0,
-         max_ctas=0):
-    """Raw kernel entry: ``out = act(alpha * op(a) @ op(b) + bias) (+ residual)``."""
+         max_ctas=0, split_k=0):
+    """Raw kernel entry: ``out = act(alpha * op(a) @ op(b) + bias) (+ residual)``.
+
+    ``split_k=0`` (auto): weight-gradient shaped products (few output tiles, very long K) are
+    split along K over CTAs -- partials are atomically added into an fp32 buffer and cast."""
     M = a.shape[1] if trans_a else a.shape[0]
     N = b.shape[0] if trans_b else b.shape[1]
+    K = a.shape[0] if trans_a else a.shape[1]
+    C = native(required=True)
+    plain = (bias is None and residual is None and aux_in is None and aux_out is None
+             and act == ACT_NONE and not accumulate and out is None
+             and (out_dtype in (None, torch.bfloat16)))
+    if split_k == 0 and plain:
+        sms = _num_sms()
+        tiles = -(-M // 128) * -(-N // 128)
+        if tiles < 2 * sms and K >= 4096:
+            split_k = max(1, min(16, int(round(2.9 * sms / tiles)), K // 512))
+    if split_k > 1 and plain:
+        acc = torch.zeros(M, N, dtype=torch.float32, device=a.device)
+        C.gemm(a, b, acc, trans_a, trans_b, None, None, None, None, 0, False, float(alpha), 128,
+               int(max_ctas), int(split_k))
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        C.cast_copy(out.view(-1), acc.view(-1), 1.0)
+        return out
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype or torch.bfloat16, device=a.device)
-    native(required=True).gemm(a, b, out, trans_a, trans_b, bias, residual, aux_in, aux_out,
-                               int(act), bool(accumulate), float(alpha), int(block_n),
-                               int(max_ctas))
+    C.gemm(a, b, out, trans_a, trans_b, bias, residual, aux_in, aux_out, int(act),
+           bool(accumulate), float(alpha), int(block_n), int(max_ctas), 1)
     return out
+
+
+_SMS = None
+
+
+def _num_sms() -> int:
+    global _SMS
+    if _SMS is None:
+        _SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _SMS
 
 
 def colsum(x2d: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:

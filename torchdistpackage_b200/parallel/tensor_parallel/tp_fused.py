@@ -59,9 +59,20 @@ class _Region:
     """A symmetric buffer + its flag words + side-stream bookkeeping."""
 
     def __init__(self, sg, nbytes: int):
-        self.buf: SymmBuffer = sg.alloc(nbytes)
+        # Ping-pong halves: use k writes half k%2.  Re-using a half two uses later needs NO
+        # cross-GPU barrier: before rank A starts use k+2 it has finished use k+1, which consumed
+        # every peer's data of use k+1, and a peer only produces use k+1 after it has finished
+        # consuming use k (stream order) -- so all readers of half k%2 are done.
+        self.half = (int(nbytes) + 4095) // 4096 * 4096
+        self.buf: SymmBuffer = sg.alloc(2 * self.half)
         self.flag_word = self.buf.alloc_words(8)     # chunk flags (AG) / tile counters (RS)
         self.nbytes = nbytes
+        self.uses = 0
+
+    def next_offset(self) -> int:
+        off = (self.uses & 1) * self.half
+        self.uses += 1
+        return off
 
 
 class FusedSpContext:
@@ -103,18 +114,17 @@ def _ag_gemm(ctx: FusedSpContext, name: str, x_shard: torch.Tensor, w: torch.Ten
     out = torch.empty(T, N, dtype=torch.bfloat16, device=x_shard.device)
     aux_out = torch.empty(T, N, dtype=torch.bfloat16, device=x_shard.device) if want_aux_out else None
     cur = torch.cuda.current_stream()
-    # everyone is done reading the previous contents of this gather buffer
-    buf.barrier(0)
+    off = reg.next_offset()                  # ping-pong half: no barrier needed (see _Region)
     ep = buf.next_epoch(reg.flag_word)
     ctx.side.wait_stream(cur)
     with torch.cuda.stream(ctx.side):
-        buf.handle.all_gather_signal(0, rows * K * 2, x_shard, reg.flag_word, ep, True,
+        buf.handle.all_gather_signal(off, rows * K * 2, x_shard, reg.flag_word, ep, True,
                                      _AG_PUSH_CTAS)
     x_shard.record_stream(ctx.side)
-    buf.handle.gemm_ag(0, rows, K, w, trans_b, out, bias, aux_out, act, reg.flag_word, ep, 0,
+    buf.handle.gemm_ag(off, rows, K, w, trans_b, out, bias, aux_out, act, reg.flag_word, ep, 0,
                        x_shard, aux_in)
     cur.wait_stream(ctx.side)
-    gathered = buf.view(0, (T, K), torch.bfloat16)
+    gathered = buf.view(off, (T, K), torch.bfloat16)
     gathered._tdp_token = (reg, ep)          # lets backward detect that the buffer was re-used
     return out, gathered, aux_out
 
@@ -124,7 +134,8 @@ def _gathered_or_regather(ctx: FusedSpContext, gathered: torch.Tensor, token, sh
     of the same module overwrites (several micro-batches in flight, activation checkpointing).
     If that happened, rebuild it from the saved shard."""
     reg, ep = token
-    if reg.buf._epochs.get(reg.flag_word, 0) == ep:
+    # ping-pong halves: the data survives exactly one later use of the region
+    if ((reg.buf._epochs.get(reg.flag_word, 0) - ep) & 0xFFFFFFFF) <= 1:
         return gathered
     full = torch.empty_like(gathered)
     dist.all_gather_into_tensor(full, shard.contiguous(), group=ctx.group)
@@ -140,10 +151,10 @@ def _gemm_rs(ctx: FusedSpContext, name: str, a: torch.Tensor, w: torch.Tensor, t
     reg = ctx.region(name, T * N * 2)
     buf = reg.buf
     out = torch.empty(rows, N, dtype=torch.bfloat16, device=a.device)
-    buf.barrier(0)       # owners finished reducing the previous contents of their staging slots
-    buf.handle.gemm_rs(a, w, trans_b, 0, reg.flag_word, 0)
+    off = reg.next_offset()                  # ping-pong staging: no barrier needed (see _Region)
+    buf.handle.gemm_rs(a, w, trans_b, off, reg.flag_word, 0)
     target = buf.next_epoch(reg.flag_word, (rows // 32) * (N // 8))
-    buf.handle.rs_reduce(0, rows, N, reg.flag_word, target, bias, residual, out, False, 0, True, 0)
+    buf.handle.rs_reduce(off, rows, N, reg.flag_word, target, bias, residual, out, False, 0, True, 0)
     return out
 
 
