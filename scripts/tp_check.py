@@ -63,6 +63,24 @@ for fused in (True, False):
     res[f"block_fused_{fused}"] = rec
     log(rec, "OK" if good else "FAIL")
 
+# ---- plain tensor parallel (no SP): row-parallel proj runs the fused GEMM -> all-reduce
+for fused in (True, False):
+    tp_fused.set_enabled(fused)
+    par = ParallelBlock(dim, num_heads=heads, sequence_parallel=False).to(dev).to(torch.bfloat16)
+    par.init_from_full(serial)
+    xp = x.clone().requires_grad_(True)
+    yp = par(xp)
+    yp.backward(gy)
+    torch.cuda.synchronize()
+    d = dim // world
+    rec = dict(fused=fused, fwd=rel(yp, ys), dx=rel(xp.grad, xs.grad),
+               dw_proj=rel(par.attn.proj.linear.weight.grad, serial.attn.proj.weight.grad[rank * d:(rank + 1) * d]),
+               db_proj=rel(par.attn.proj.linear.bias.grad, serial.attn.proj.bias.grad))
+    good = all(v < 4e-2 for k_, v in rec.items() if k_ != "fused")
+    ok &= good
+    res[f"block_nosp_fused_{fused}"] = rec
+    log("no-SP", rec, "OK" if good else "FAIL")
+
 # ---- timing: config #3-like transformer (4 blocks), fused vs NCCL path
 def step_time(fused, dim=4096, heads=32, depth=4, B=4, N=2048, iters=6, warm=3):
     tp_fused.set_enabled(fused)

@@ -429,3 +429,40 @@ def _w_moe_layer(rank, world):
 
 def test_moe_layer_expert_parallel_matches_serial():
     run_distributed(_w_moe_layer, 2)
+
+
+# ------------------------------------------------------------------ full mixed parallel (config #5)
+def _w_mixed_parallel_gpt(rank, world):
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.models.gpt2 import GPT2Config
+    from torchdistpackage_b200.models.gpt2_parallel import GPT2PipelineStage
+    from torchdistpackage_b200.parallel import forward_backward
+    tdp.tpc.setup_process_groups([("data", world // 4), ("pipe", 2), ("tensor", 2)])
+    cfg = GPT2Config(vocab_size=128, n_layer=4, n_head=4, d_model=64, seq_len=32)
+    tdp.fix_rand(0)
+    stage = GPT2PipelineStage(cfg, tp_group=tdp.tpc.get_group("tensor"), sequence_parallel=True)
+    opt = tdp.Bf16ZeroOptimizer(torch.optim.AdamW(stage.parameters(), lr=1e-2),
+                                dp_group=tdp.tpc.get_group("data"), overlap_comm=False)
+    torch.manual_seed(5 + tdp.tpc.get_dp_rank())
+    tok = torch.randint(0, 128, (8, 33))
+    losses = []
+    for it in range(6):
+        out = forward_backward(opt, stage.forward_fn(), None,
+                               stage.stage_inputs(tok[:, :-1], tok[:, 1:]), num_microbatches=2,
+                               dtype=torch.float32)
+        stage.allreduce_replicated_grads()
+        opt.step()
+        if stage.last:
+            losses.append(float(out))
+    if stage.last:
+        assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    # tensor-parallel replicas of replicated parameters must stay identical
+    if stage.last:
+        w = stage.ln_f.weight.detach().clone()
+        ws = [torch.empty_like(w) for _ in range(2)]
+        dist.all_gather(ws, w, group=tdp.tpc.get_group("tensor"))
+        assert torch.allclose(ws[0], ws[1], atol=1e-6)
+
+
+def test_mixed_parallel_gpt_dp_pp_tp_zero():
+    run_distributed(_w_mixed_parallel_gpt, 8)

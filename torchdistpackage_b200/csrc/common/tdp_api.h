@@ -142,6 +142,10 @@ void launch_scale_(void* x, int dtype, size_t numel, float scale, const float* s
 void launch_cast_copy(void* dst, int dst_dtype, const void* src, int src_dtype, size_t numel,
                       float scale, cudaStream_t stream);
 
+// strided copy of rows (row_bytes % 16 == 0, contiguous rows) indexed by (i0,i1,i2); byte strides
+void launch_rows_copy(const void* src, void* dst, int n0, int n1, int n2, int row_bytes, long s0,
+                      long s1, long s2, long d0, long d1, long d2, cudaStream_t stream);
+
 // LayerNorm over the last dim of bf16 [rows, cols]; saves mean / rstd (fp32) for backward
 void launch_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
                           void* y, void* resid_out, float* mean, float* rstd, int rows, int cols,

@@ -373,14 +373,28 @@ colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, in
   }
 }
 
-__global__ void colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial,
-                                             int cols, void* __restrict__ out, int out_bf16) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] = sum_p partial[p][c]: block = 8 warps x 32 columns; warp w sums partials w, w+8, ...
+// (coalesced 128-byte rows), then the 8 warp sums meet in shared memory.
+__global__ void __launch_bounds__(256)
+colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int cols,
+                             void* __restrict__ out, int out_bf16) {
+  __shared__ float sred[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int p = 0; p < n_partial; ++p) acc += partial[static_cast<size_t>(p) * cols + c];
-  if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[c] = __float2bfloat16_rn(acc);
-  else reinterpret_cast<float*>(out)[c] = acc;
+  if (c < cols) {
+#pragma unroll 4
+    for (int p = w; p < n_partial; p += 8) acc += partial[static_cast<size_t>(p) * cols + c];
+  }
+  sred[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sred[i][lane];
+    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[c] = __float2bfloat16_rn(t);
+    else reinterpret_cast<float*>(out)[c] = t;
+  }
 }
 
 // partial column sums: block b handles rows [b*rows_per_block, ...), thread = 8 columns
@@ -520,8 +534,8 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
 
 void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols, void* out,
                                   int out_bf16, cudaStream_t stream) {
-  colsum_partial_reduce_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(partial, n_partial, cols,
-                                                                      out, out_bf16);
+  colsum_partial_reduce_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partial, n_partial, cols, out,
+                                                                    out_bf16);
 }
 
 void launch_colsum(const void* x, int rows, int cols, int ld, float* scratch, void* out,

@@ -121,6 +121,43 @@ TDP_DEVICE int remap_m_block(const GemmParams& p, int m_blk) {
   return chunk * blocks_per_chunk + r;
 }
 
+// Work iterator shared by the three warp roles (they must all walk the same sequence).
+//   data-parallel (split_k == 1): output tiles blockIdx.x, +gridDim.x, ... over the full K range;
+//   stream-K      (split_k  > 1): the flattened (tile, k-block) space is cut into equal
+//   contiguous shares of `k_blocks_per_split` k-blocks per CTA; a share crosses at most a few
+//   tile boundaries and every segment is accumulated into the fp32 output with vector atomics.
+struct WorkIter {
+  int tile, kb0, kb1;
+  int pos, end;
+  TDP_DEVICE explicit WorkIter(const GemmParams& p) : tile(0), kb0(0), kb1(0) {
+    if (p.split_k > 1) {
+      const long total = static_cast<long>(p.num_m_blocks) * p.num_n_blocks * p.num_k_blocks;
+      const long b = static_cast<long>(blockIdx.x) * p.k_blocks_per_split;
+      pos = static_cast<int>(b < total ? b : total);
+      end = static_cast<int>(b + p.k_blocks_per_split < total ? b + p.k_blocks_per_split : total);
+    } else {
+      pos = blockIdx.x;
+      end = p.num_m_blocks * p.num_n_blocks;
+    }
+  }
+  TDP_DEVICE bool next(const GemmParams& p) {
+    if (pos >= end) return false;
+    if (p.split_k > 1) {
+      tile = pos / p.num_k_blocks;
+      kb0 = pos - tile * p.num_k_blocks;
+      const int len = min(p.num_k_blocks - kb0, end - pos);
+      kb1 = kb0 + len;
+      pos += len;
+    } else {
+      tile = pos;
+      kb0 = 0;
+      kb1 = p.num_k_blocks;
+      pos += gridDim.x;
+    }
+    return true;
+  }
+};
+
 TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Everything between the accumulator and the store for one thread-row x 32 columns.
@@ -291,11 +328,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (WorkIter it(p); it.next(p);) {
         int m_blk, n_blk;
-        tile_to_mn(p, tile / p.split_k, m_blk, n_blk);
-        const int kb0 = (tile % p.split_k) * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+        tile_to_mn(p, it.tile, m_blk, n_blk);
+        const int kb0 = it.kb0, kb1 = it.kb1;
         m_blk = remap_m_block(p, m_blk);
         int m0 = m_blk * kBlockM;
         const CUtensorMap* amap = &tmap_a;
@@ -354,13 +390,12 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (WorkIter it(p); it.next(p);) {
       // wait until the epilogue has drained this accumulator stage
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      const int kb0 = (tile % p.split_k) * p.k_blocks_per_split;
-      const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
+      const int kb0 = it.kb0, kb1 = it.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -396,9 +431,9 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     int store_buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (WorkIter it(p); it.next(p);) {
       int m_blk, n_blk;
-      tile_to_mn(p, tile / p.split_k, m_blk, n_blk);
+      tile_to_mn(p, it.tile, m_blk, n_blk);
       m_blk = remap_m_block(p, m_blk);
       const int row_in_tile = quad * 32 + lane;
       const int row = m_blk * kBlockM + row_in_tile;

@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from ..ops import fused as F_ops
 from ..ops import linear as L_ops
+from ..ops.attention import packed_attention
 
 
 @dataclass
@@ -91,9 +92,7 @@ class GPT2Block(nn.Module):
         B, T, D = x.shape
         h = F_ops.layer_norm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
         qkv = L_ops.linear(h, self.w_qkv, self.b_qkv, layout="kn")
-        q, k, v = qkv.view(B, T, 3, self.n_head, D // self.n_head).permute(2, 0, 3, 1, 4)
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)        # [B, h, T, dh]
-        o = o.transpose(1, 2).reshape(B, T, D)
+        o = packed_attention(qkv, self.n_head, causal=True)                # [B, T, D], no layout copies
         x = L_ops.linear(o, self.w_proj, self.b_proj, layout="kn", residual=x)   # x + proj(o)
         h = F_ops.layer_norm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
         return L_ops.mlp(h, self.w_fc1, self.b_fc1, self.w_fc2, self.b_fc2, layout="kn",

@@ -25,6 +25,9 @@ def _import():
 def native(required: bool = False):
     """Return the extension module, or ``None`` if unavailable (and not ``required``)."""
     global _mod, _tried
+    if os.environ.get("TDP_DISABLE_NATIVE") == "1" and not required:
+        # explicit opt-out (used by baseline harnesses that must run on plain torch kernels)
+        return None
     if _mod is not None:
         return _mod
     with _lock:

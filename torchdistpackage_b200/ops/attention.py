@@ -1,0 +1,67 @@
+"""Attention over a packed qkv projection without layout round trips.
+
+The attention core itself is the library flash kernel (``scaled_dot_product_attention``: cuDNN's
+sm_100 kernel on B200) -- see DESIGN.md for the status of a tcgen05 attention kernel.  What is
+ours is everything around it: q / k / v are strided *views* of the packed ``[B, T, 3*H*Dh]`` GEMM
+output (no split copies), the ``[B,H,T,Dh] -> [B,T,H*Dh]`` output permute and, in backward, the
+``dO`` permute and the scatter of dq / dk / dv into ONE packed ``[B, T, 3*H*Dh]`` gradient are
+16-byte-vectorised row-copy kernels (csrc/fused/layout.cu) instead of the generic strided-copy
+and ``cat`` kernels autograd would insert (3.5 ms of a 26 ms GPT-2-small step in the plain-torch
+reference arm).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from ._loader import native
+
+
+class _PackedAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_head: int, causal: bool, scale: Optional[float]):
+        C = native()
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // n_head
+        qkv5 = qkv.view(B, T, 3, n_head, dh)
+        with torch.enable_grad():
+            q, k, v = (qkv5[:, :, i].transpose(1, 2).detach().requires_grad_(True) for i in range(3))
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale)
+        out = torch.empty(B, T, n_head, dh, dtype=qkv.dtype, device=qkv.device)
+        C.permute_rows_copy(out.transpose(1, 2), o)
+        ctx.graph = (q, k, v, o)
+        ctx.dims = (B, T, n_head, dh)
+        return out.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        C = native()
+        B, T, H, dh = ctx.dims
+        q, k, v, o = ctx.graph
+        ctx.graph = None
+        do = torch.empty(B, H, T, dh, dtype=dout.dtype, device=dout.device)
+        C.permute_rows_copy(do, dout.reshape(B, T, H, dh).transpose(1, 2))
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
+        dqkv = torch.empty(B, T, 3, H, dh, dtype=dout.dtype, device=dout.device)
+        for i, g in enumerate((dq, dk, dv)):
+            if g.stride(3) != 1:
+                g = g.contiguous()
+            C.permute_rows_copy(dqkv[:, :, i].transpose(1, 2), g)
+        return dqkv.view(B, T, 3 * H * dh), None, None, None
+
+
+def packed_attention(qkv: torch.Tensor, n_head: int, causal: bool = True,
+                     scale: Optional[float] = None) -> torch.Tensor:
+    """``qkv`` ``[B, T, 3*H*Dh]`` (q | k | v along the last dim) -> ``[B, T, H*Dh]``."""
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    dh = D // n_head
+    if native() is not None and qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16) \
+            and (dh * qkv.element_size()) % 16 == 0 and qkv.is_contiguous():
+        return _PackedAttnFn.apply(qkv, n_head, causal, scale)
+    q, k, v = qkv.view(B, T, 3, n_head, dh).permute(2, 0, 3, 1, 4)
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale)
+    return o.transpose(1, 2).reshape(B, T, D)

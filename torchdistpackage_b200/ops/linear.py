@@ -58,14 +58,16 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
              and act == ACT_NONE and not accumulate and out is None
              and (out_dtype in (None, torch.bfloat16)))
     if split_k == 0 and plain:
+        # stream-K whenever the 128x256 output tiles cannot fill the machine for >= ~3 waves and K
+        # is long enough to amortise the fp32 atomics (weight gradients: K = tokens)
         sms = _num_sms()
-        tiles = -(-M // 128) * -(-N // 128)
-        if tiles < 2 * sms and K >= 4096:
-            split_k = max(1, min(16, int(round(2.9 * sms / tiles)), K // 512))
+        tiles = -(-M // 128) * -(-N // 256)
+        if tiles < 3 * sms and K >= 2048 and tiles % sms != 0:
+            split_k = 2
     if split_k > 1 and plain:
         acc = torch.zeros(M, N, dtype=torch.float32, device=a.device)
-        C.gemm(a, b, acc, trans_a, trans_b, None, None, None, None, 0, False, float(alpha), 128,
-               int(max_ctas), int(split_k))
+        C.gemm(a, b, acc, trans_a, trans_b, None, None, None, None, 0, False, float(alpha),
+               256 if N > 128 else 128, int(max_ctas), int(split_k))
         out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
         C.cast_copy(out.view(-1), acc.view(-1), 1.0)
         return out

@@ -158,6 +158,51 @@ def _gemm_rs(ctx: FusedSpContext, name: str, a: torch.Tensor, w: torch.Tensor, t
     return out
 
 
+def _gemm_ar(ctx: FusedSpContext, name: str, a: torch.Tensor, w: torch.Tensor, trans_b: bool,
+             bias=None) -> torch.Tensor:
+    """out_full [T, N] = all_reduce(a @ op(w)) + bias, fused: the GEMM epilogue scatters tiles to
+    the chunk owners (as in GEMM->RS); each owner's reduce kernel then *broadcasts* its reduced
+    rows to every rank with ``multimem.st`` (two-shot all-reduce whose first shot is the GEMM
+    epilogue).  Returns a view of the symmetric output buffer (valid until the call after next)."""
+    T, _ = a.shape
+    rows = T // ctx.tp
+    N = w.shape[0] if trans_b else w.shape[1]
+    nb = T * N * 2
+    reg = ctx.region(name, 2 * nb)           # [staging | output] per ping-pong half
+    buf = reg.buf
+    off = reg.next_offset()
+    buf.handle.gemm_rs(a, w, trans_b, off, reg.flag_word, 0)
+    target = buf.next_epoch(reg.flag_word, (rows // 32) * (N // 8))
+    buf.handle.rs_reduce(off, rows, N, reg.flag_word, target, bias, None, None, True, off + nb,
+                         True, 0)
+    buf.barrier(0)                           # every owner's broadcast has landed everywhere
+    return buf.view(off + nb, (T, N), torch.bfloat16)
+
+
+class _LinearArFn(torch.autograd.Function):
+    """Row-parallel linear without sequence parallelism: y = all_reduce(a_local @ W_local) + b."""
+
+    @staticmethod
+    def forward(ctx, fctx, slot, a, w, bias):
+        out = _gemm_ar(fctx, slot + ":ar", a, w, False, bias)
+        ctx.save_for_backward(a, w)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        da = L.gemm(dy, w, trans_b=True)          # the all-reduce is an identity in backward
+        dw = L.gemm(a, dy, trans_a=True)
+        db = L.colsum(dy) if ctx.has_bias else None
+        return None, None, da, dw, db
+
+
+def linear_ar(fctx: FusedSpContext, a: torch.Tensor, w, bias, slot: str = "out"):
+    return _LinearArFn.apply(fctx, slot, a.contiguous(), w, bias)
+
+
 # ------------------------------------------------------------------------------------------
 # autograd functions
 # ------------------------------------------------------------------------------------------

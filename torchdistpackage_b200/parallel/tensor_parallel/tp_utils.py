@@ -285,6 +285,17 @@ class RowParallelLinear(nn.Module):
         self.linear.weight.tensor_model_parallel = True
 
     def forward(self, x):
+        if not self.sequence_parallel and self.tp_world_size > 1:
+            # fused GEMM -> all-reduce over NVSwitch (epilogue scatter + multicast broadcast)
+            from . import tp_fused
+            rows = x.numel() // x.shape[-1]
+            if tp_fused.usable(x, self.tp_world_size) and rows % (128 * self.tp_world_size) == 0 \
+                    and self.fout % 8 == 0:
+                if getattr(self, "_fused", None) is None:
+                    self._fused = tp_fused.FusedSpContext(get_tp_group())
+                y = tp_fused.linear_ar(self._fused, x.reshape(rows, x.shape[-1]),
+                                       self.linear.weight, self.linear.bias)
+                return y.view(*x.shape[:-1], self.fout)
         out = self.linear(x, bias_override=None)     # bias is added once, after the reduction
         if not self.sequence_parallel:
             out = reduce_from_tensor_parallel_region(out)
