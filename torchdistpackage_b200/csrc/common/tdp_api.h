@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 namespace tdp {
 
 constexpr int kApiMaxPeers = 8;
@@ -170,5 +172,17 @@ void launch_cross_entropy_fwd_bwd(void* logits, int rows, int vocab, int ld, con
 void launch_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                            int B, int S, int H, int D, int q_stride, int kv_stride, int o_stride,
                            int causal, float scale, cudaStream_t stream);
+
+// ------------------------------------------------------------------ native symmetric memory
+// (symm/symm_vmm.cpp): CUDA VMM allocations exported as POSIX fds, peer mapping, NVLS multicast
+bool vmm_granularity(int device, int num_devices, uint64_t* gran, std::string& err);
+bool vmm_alloc(uint64_t size, int device, uint64_t* handle, uint64_t* ptr, int* fd, std::string& err);
+bool vmm_import(int fd, uint64_t size, int device, uint64_t* handle, uint64_t* ptr, std::string& err);
+bool mc_create(uint64_t size, int num_devices, uint64_t* handle, int* fd, std::string& err);
+bool mc_import(int fd, uint64_t* handle, std::string& err);
+bool mc_add_device(uint64_t mc_handle, int device, std::string& err);
+bool mc_bind_and_map(uint64_t mc_handle, uint64_t mem_handle, uint64_t size, int device,
+                     uint64_t* mc_ptr, std::string& err);
+bool vmm_unmap_release(uint64_t handle, uint64_t ptr, uint64_t size, std::string& err);
 
 }  // namespace tdp

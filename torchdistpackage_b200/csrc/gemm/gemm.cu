@@ -98,8 +98,8 @@ int g_num_sms = 0;
 
 template <int BLOCK_N>
 cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta_local,
-                        const GemmStoreMaps& sm, const GemmParams& p, int grid,
-                        cudaStream_t stream) {
+                        const CUtensorMap& t_in, const CUtensorMap& t_aux, const GemmStoreMaps& sm,
+                        const GemmParams& p, int grid, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -109,8 +109,8 @@ cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(ta, tb, ta_local,
-                                                                                  sm, p);
+  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(
+      ta, tb, ta_local, t_in, t_aux, sm, p);
   return cudaGetLastError();
 }
 
@@ -240,6 +240,28 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     p.use_tma_store = 1;
   }
 
+  // row-wise epilogue operands travel through TMA as well (no strided 16-byte LSU traffic):
+  //   input  = residual or the dGELU pre-activation, loaded per [128 x 64] sub-tile
+  //   output = the pre-activation copy (aux_out), stored from the second staging buffer
+  CUtensorMap t_in = ta, t_aux = ta;
+  p.epi_in_tma = 0;
+  p.epi_aux_tma = 0;
+  if (p.use_tma_store && p.comm_mode != COMM_RS_SCATTER) {
+    const bool has_res = g.residual != nullptr;
+    const bool has_dgelu = (g.act == ACT_DGELU_TANH || g.act == ACT_DGELU_ERF) && g.aux_in != nullptr;
+    if (has_res != has_dgelu) {       // exactly one row-wise input
+      const void* base = has_res ? g.residual : g.aux_in;
+      const int ld = has_res ? g.ld_res : g.ld_aux;
+      if ((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0 &&
+          make_tmap_2d(&t_in, base, g.N, g.M, ld, kStoreCols, kBlockM))
+        p.epi_in_tma = has_res ? 1 : 2;
+    }
+    if (g.aux_out != nullptr && p.epi_in_tma == 0 &&
+        (reinterpret_cast<uintptr_t>(g.aux_out) & 15) == 0 && g.ld_aux % 8 == 0 &&
+        make_tmap_2d(&t_aux, g.aux_out, g.N, g.M, g.ld_aux, kStoreCols, kBlockM))
+      p.epi_aux_tma = 1;
+  }
+
   // split-K (weight-gradient shapes: few output tiles, very long K): partials are added with
   // vector atomics into an fp32 output that the caller zero-initialised (or accumulates into)
   p.split_k = 1;
@@ -265,8 +287,9 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     p.k_blocks_per_split = static_cast<int>(share);
     grid = static_cast<int>((total + share - 1) / share);
   }
-  cudaError_t e = (block_n == 256) ? launch_impl<256>(ta, tb, ta_local, sm, p, grid, stream)
-                                   : launch_impl<128>(ta, tb, ta_local, sm, p, grid, stream);
+  cudaError_t e = (block_n == 256)
+                      ? launch_impl<256>(ta, tb, ta_local, t_in, t_aux, sm, p, grid, stream)
+                      : launch_impl<128>(ta, tb, ta_local, t_in, t_aux, sm, p, grid, stream);
   if (e != cudaSuccess) {
     snprintf(msg, sizeof(msg), "gemm launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);

@@ -19,8 +19,11 @@ namespace tdp {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;     // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumEpilogueWarps = 4;
-constexpr int kGemmThreads = 32 * (2 + kNumEpilogueWarps);  // warp0 TMA, warp1 MMA, warps2-5 epi
+// 8 epilogue warps: two per TMEM lane quadrant (each takes one 32-column half of every 64-column
+// sub-tile) -> two warps per SM sub-partition, so the epilogue math (GELU, dGELU) can hide its own
+// latency and keeps up with the MMA pipe.
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kGemmThreads = 32 * (2 + kNumEpilogueWarps);  // warp0 TMA, warp1 MMA, warps2-9 epi
 constexpr int kMaxPeers = 8;
 constexpr int kStoreCols = 64;                         // TMA-store sub-tile: 128 rows x 64 cols
 constexpr int kStoreBytes = kBlockM * kStoreCols * 2;  // 16 KiB, 128B-swizzled
@@ -54,6 +57,8 @@ struct GemmParams {
   int c_fp32;
   int accumulate;   // C += result (fp32 or bf16 read-modify-write)
   int use_tma_store;
+  int epi_in_tma;    // 1: residual, 2: dGELU input -- the [128 x 64] sub-tile arrives through TMA
+  int epi_aux_tma;   // pre-activation copy (aux_out) leaves through smem + TMA store
   float alpha;
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, ld_res] or null
@@ -158,11 +163,16 @@ struct WorkIter {
   }
 };
 
-TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // Everything between the accumulator and the store for one thread-row x 32 columns.
 // `full` = the 32 columns are all inside N.
-TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int col0, bool full) {
+// `in_row` (optional): this thread's row of the TMA-loaded, 128B-swizzled input sub-tile (residual
+// or dGELU pre-activation) -- chunk c of the 64-column sub-tile lives at (c ^ swz) * 16.
+// `z_row` (optional): same layout, receives the pre-activation copy instead of a global store.
+TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int col0, bool full,
+                              const uint8_t* in_row = nullptr, uint8_t* z_row = nullptr, int h = 0,
+                              int swz = 0) {
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -175,7 +185,15 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int 
       }
     }
   }
-  if (p.aux_out != nullptr) {
+  if (z_row != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(z_row + (((h * 4 + j) ^ swz) * 16)) = o;
+    }
+  } else if (p.aux_out != nullptr) {
     __nv_bfloat16* arow = p.aux_out + static_cast<size_t>(row) * p.ld_aux + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -198,7 +216,9 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int 
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       if (full || col0 + j + 8 <= p.N) {
-        const uint4 z = *reinterpret_cast<const uint4*>(zrow + j);
+        const uint4 z = (in_row != nullptr)
+            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
+            : *reinterpret_cast<const uint4*>(zrow + j);
         float zz[8];
         float2 t;
         t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
@@ -216,7 +236,9 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int 
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       if (full || col0 + j + 8 <= p.N) {
-        const uint4 z = *reinterpret_cast<const uint4*>(rrow + j);
+        const uint4 z = (in_row != nullptr)
+            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
+            : *reinterpret_cast<const uint4*>(rrow + j);
         float2 t;
         t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
         t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
@@ -281,6 +303,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_a_local,
+                       const __grid_constant__ CUtensorMap tmap_in,
+                       const __grid_constant__ CUtensorMap tmap_aux,
                        const __grid_constant__ GemmStoreMaps store_maps, const GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int kStages = S::kStages;
@@ -298,7 +322,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* in_bar = bars + 2 * kStages + 4;       // epilogue input sub-tile loads (2 buffers)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
   const int warp_idx = threadIdx.x / 32;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;   // work items
@@ -313,6 +338,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], kNumEpilogueWarps);
+      mbar_init(&in_bar[i], 1);
     }
     fence_barrier_init();
   } else if (warp_idx == 1) {
@@ -426,11 +452,13 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ================================ epilogue warps ================================
     // A warp may only touch TMEM lanes [32*(warp_idx%4), +32).
     const int quad = warp_idx & 3;
+    const int half = (warp_idx - 2) >> 2;     // which 32-column half of a sub-tile this warp owns
     const int lane = threadIdx.x & 31;
     const bool issuer = (warp_idx == 2) && (lane == 0);   // the thread that owns the TMA stores
     int acc = 0;
     uint32_t acc_phase = 0;
     int store_buf = 0;
+    uint32_t in_phase = 0;      // phase bits of in_bar[0..1]
     for (WorkIter it(p); it.next(p);) {
       int m_blk, n_blk;
       tile_to_mn(p, it.tile, m_blk, n_blk);
@@ -445,7 +473,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
 
       if (p.use_tma_store) {
-        // ---- TMEM -> registers -> swizzled smem -> TMA store (128 rows x 64 cols at a time)
+        // ---- TMEM -> registers -> swizzled smem -> TMA store (128 rows x 64 cols at a time).
+        // Row-wise epilogue operands never touch the LSU with strided 16-byte accesses: the
+        // residual / dGELU input sub-tile is TMA-loaded into the staging buffer (prefetched one
+        // sub-tile ahead) and combined in place; the pre-activation copy leaves through the second
+        // staging buffer and its own TMA store.
         const CUtensorMap* cmap = &store_maps.m[0];
         int dst_rank = -1;
         int store_row0 = m_blk * kBlockM;
@@ -454,15 +486,44 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           cmap = &store_maps.m[dst_rank];
           store_row0 -= dst_rank * p.rows_per_chunk;
         }
+        const bool in_tma = p.epi_in_tma != 0;
+        const bool aux_tma = p.epi_aux_tma != 0;
+        const int swz = row_in_tile & 7;
+        const int n_sub = (min(BLOCK_N, p.N - n0) + kStoreCols - 1) / kStoreCols;
+        if (in_tma && issuer) {
+          tma_store_wait_read<0>();                         // both staging buffers are free
+          mbar_expect_tx(&in_bar[store_buf], kStoreBytes);
+          tma_load_2d(&tmap_in, &in_bar[store_buf], smem_store + store_buf * kStoreBytes, n0,
+                      m_blk * kBlockM);
+        }
 #pragma unroll 1
-        for (int sc = 0; sc < BLOCK_N; sc += kStoreCols) {
-          if (n0 + sc >= p.N) break;                          // warp-uniform
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const int sc = sub * kStoreCols;
           uint8_t* sbuf = smem_store + store_buf * kStoreBytes;
-          // the store issued two sub-tiles ago must have finished reading this buffer
-          if (issuer) tma_store_wait_read<1>();
+          uint8_t* obuf = smem_store + (store_buf ^ 1) * kStoreBytes;
+          if (issuer) {
+            if (in_tma) {
+              tma_store_wait_read<0>();                     // store(sub-1) finished reading obuf
+              if (sub + 1 < n_sub) {                        // prefetch the next input sub-tile
+                mbar_expect_tx(&in_bar[store_buf ^ 1], kStoreBytes);
+                tma_load_2d(&tmap_in, &in_bar[store_buf ^ 1], obuf, n0 + sc + kStoreCols,
+                            m_blk * kBlockM);
+              }
+            } else if (aux_tma) {
+              tma_store_wait_read<0>();                     // both buffers are written below
+            } else {
+              tma_store_wait_read<1>();                     // the store two sub-tiles ago
+            }
+          }
           epi_bar_sync();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          if (in_tma) {
+            mbar_wait(&in_bar[store_buf], (in_phase >> store_buf) & 1u);
+            in_phase ^= (1u << store_buf);
+          }
+          uint8_t* srow = sbuf + row_in_tile * 128;
+          uint8_t* orow = obuf + row_in_tile * 128;
+          {
+            const int h = half;
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + sc + h * 32, r);
             tmem_ld_wait();
@@ -470,9 +531,11 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-            if (row_ok && col0 < p.N) epilogue_math(p, v, row, col0, col0 + 32 <= p.N);
+            if (row_ok && col0 < p.N)
+              epilogue_math(p, v, row, col0, col0 + 32 <= p.N, in_tma ? srow : nullptr,
+                            aux_tma ? srow : nullptr, h, swz);
             // row r of the staging tile: 128 bytes, 16-byte chunk c stored at (c ^ (r & 7))
-            uint8_t* srow = sbuf + row_in_tile * 128;
+            uint8_t* wrow = aux_tma ? orow : srow;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -480,11 +543,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
               o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
               o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
               o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              const int chunk = (h * 4 + j) ^ (row_in_tile & 7);
-              *reinterpret_cast<uint4*>(srow + chunk * 16) = o;
+              *reinterpret_cast<uint4*>(wrow + (((h * 4 + j) ^ swz) * 16)) = o;
             }
           }
-          if (sc + kStoreCols >= BLOCK_N || n0 + sc + kStoreCols >= p.N) {
+          if (sub == n_sub - 1) {
             // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -493,10 +555,15 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the TMA engine
           epi_bar_sync();
           if (issuer) {
-            tma_store_2d(cmap, sbuf, n0 + sc, store_row0);
+            if (aux_tma) {
+              tma_store_2d(&tmap_aux, sbuf, n0 + sc, m_blk * kBlockM);
+              tma_store_2d(cmap, obuf, n0 + sc, store_row0);
+            } else {
+              tma_store_2d(cmap, sbuf, n0 + sc, store_row0);
+            }
             tma_store_commit();
           }
-          store_buf ^= 1;
+          if (!aux_tma) store_buf ^= 1;
         }
         if (p.comm_mode == COMM_RS_SCATTER && issuer) {
           // all of this tile's bytes must have landed in the owner's memory before the counter
@@ -513,7 +580,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint8_t* c_row = reinterpret_cast<uint8_t*>(p.C) +
                          static_cast<size_t>(row) * p.ldc * (p.c_fp32 ? 4 : 2);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = half * 32; c < BLOCK_N; c += 64) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c, r);
           tmem_ld_wait();

@@ -32,23 +32,102 @@ def _dtype_code(dtype: torch.dtype) -> int:
     raise TypeError(f"symmetric collectives support bf16 / fp32, got {dtype}")
 
 
+def _pidfd_getfd(pid: int, fd: int) -> int:
+    """Duplicate file descriptor ``fd`` of process ``pid`` into this process (Linux >= 5.6)."""
+    import ctypes
+    import os
+    pidfd = os.pidfd_open(pid)
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        new = libc.syscall(438, pidfd, fd, 0)       # __NR_pidfd_getfd (x86_64 / aarch64)
+        if new < 0:
+            raise OSError(ctypes.get_errno(), "pidfd_getfd failed")
+        return int(new)
+    finally:
+        os.close(pidfd)
+
+
+def _native_symm_alloc(pg, nbytes: int, want_multicast: bool):
+    """Our own symmetric allocation (csrc/symm/symm_vmm.cpp): VMM allocation exported as a POSIX
+    fd, fds exchanged with ``pidfd_getfd`` over the process group, every peer's memory mapped
+    here, one multicast object bound to all of them.  Layout: [data | 64 KiB signal pad].
+    Returns ``(tensor, buffer_ptrs, signal_ptrs, multicast_ptr)``."""
+    import os
+    C = native(required=True)
+    rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+    dev = torch.cuda.current_device()
+    gran = C.vmm_granularity(dev, world)
+    data = (nbytes + 4095) // 4096 * 4096
+    total = (data + SIGNAL_PAD_BYTES + gran - 1) // gran * gran
+    h, ptr, fd = C.vmm_alloc(total, dev)
+    infos = [None] * world
+    dist.all_gather_object(infos, (os.getpid(), fd), group=pg)
+    ptrs = []
+    for r, (pid, pfd) in enumerate(infos):
+        if r == rank:
+            ptrs.append(ptr)
+        else:
+            dup = _pidfd_getfd(pid, pfd)
+            _, pp = C.vmm_import(dup, total, dev)
+            os.close(dup)
+            ptrs.append(pp)
+    mc_ptr = 0
+    if want_multicast:
+        ok = 1
+        try:
+            if rank == 0:
+                mch, mcfd = C.mc_create(total, world)
+                box = [(os.getpid(), mcfd)]
+            else:
+                box = [None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0), group=pg)
+            if rank != 0:
+                dup = _pidfd_getfd(box[0][0], box[0][1])
+                mch = C.mc_import(dup)
+                os.close(dup)
+            C.mc_add_device(mch, dev)
+        except Exception:           # pragma: no cover - depends on driver / fabric support
+            ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)      # everyone added its device
+        if int(flag.item()) == 1:
+            mc_ptr = C.mc_bind_and_map(mch, h, total, dev)
+    dist.barrier(group=pg)          # peers have imported: the exporter may close its fds
+    os.close(fd)
+    whole = C.tensor_from_ptr(ptr, total, dev)
+    whole.zero_()
+    tensor = whole[:nbytes]
+    tensor._tdp_keepalive = whole
+    return tensor, ptrs, [p + data for p in ptrs], mc_ptr
+
+
 class SymmBuffer:
     """One symmetric allocation.  ``tensor`` is this rank's memory (uint8)."""
 
     def __init__(self, group: "SymmGroup", nbytes: int):
-        import torch.distributed._symmetric_memory as symm_mem
+        import os
         self.group = group
         self.nbytes = int(nbytes)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.tensor = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=dev)
-        hdl = symm_mem.rendezvous(self.tensor, group.pg)
-        self._torch_handle = hdl
-        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-        if group.disable_multicast:
-            mc = 0
-        self.handle = native(required=True).SymmHandle(
-            [int(p) for p in hdl.buffer_ptrs], [int(p) for p in hdl.signal_pad_ptrs], mc,
-            int(hdl.rank), int(hdl.world_size), self.nbytes, dev.index)
+        backend = os.environ.get("TDP_SYMM_BACKEND", "torch")
+        if backend == "native" and hasattr(native(required=True), "vmm_alloc"):
+            self.tensor, bufs, sigs, mc = _native_symm_alloc(group.pg, self.nbytes,
+                                                            not group.disable_multicast)
+            self.handle = native(required=True).SymmHandle(bufs, sigs, mc, group.rank, group.world,
+                                                           self.nbytes, dev.index)
+            self.backend = "native"
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.tensor = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=dev)
+            hdl = symm_mem.rendezvous(self.tensor, group.pg)
+            self._torch_handle = hdl
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if group.disable_multicast:
+                mc = 0
+            self.handle = native(required=True).SymmHandle(
+                [int(p) for p in hdl.buffer_ptrs], [int(p) for p in hdl.signal_pad_ptrs], mc,
+                int(hdl.rank), int(hdl.world_size), self.nbytes, dev.index)
+            self.backend = "torch"
         self.has_multicast = bool(mc)
         self._next_word = USER_WORD_BASE
         self._epochs: Dict[int, int] = {}
