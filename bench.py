@@ -65,6 +65,24 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        # NVML in-process (20 ms period) when available, else an `nvidia-smi -lms` child
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:        # CUDA_VISIBLE_DEVICES-proof: look the device up by UUID
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.samples = []
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
@@ -74,11 +92,42 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _stop_nvml(self) -> dict:
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        reasons = set()
+        for _, _, _, rs in self.samples:
+            for bit, name in names.items():
+                if rs & bit:
+                    reasons.add(name)
+        sm = sorted(x[0] for x in self.samples)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None,
+                "sm_max_mhz": float(max(x[1] for x in self.samples)) if sm else None,
+                "power_w_max": max(x[2] for x in self.samples) if sm else None,
+                "samples": len(sm), "source": "nvml", "reasons": sorted(reasons)}
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if getattr(self, "nvml", None) is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

@@ -41,7 +41,8 @@ else:
 
 rank, world = dist.get_rank(), dist.get_world_size()
 dev = torch.device("cuda", torch.cuda.current_device())
-pkg.tpc.setup_process_groups([("tensor", world)])
+# (the reference's hybrid-group pass needs a "data" entry: process_topo.py:114)
+pkg.tpc.setup_process_groups([("tensor", world), ("data", 1)])
 tp_utils.set_tp_group(pkg.tpc.get_group("tensor"))
 
 torch.manual_seed(0)

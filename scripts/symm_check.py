@@ -163,6 +163,27 @@ try:
 except Exception as ex:
     import traceback; traceback.print_exc(); ok = False; res["ag_gemm_error"] = repr(ex)
 
+# ------------------------------------------------------------------ all-gather *inside* the GEMM
+def run_ag_gemm_inkernel():
+    buf.barrier(2)
+    ep = buf.next_epoch(flag_word)
+    buf.handle.gemm_ag(ag_off, rows, Kf, w2, False, cfull, None, None, 0, flag_word, ep, 0, xs, None,
+                       True, True)
+try:
+    buf.view(ag_off, (T, Kf), torch.bfloat16).zero_(); cfull.zero_()
+    torch.cuda.synchronize(); dist.barrier()
+    run_ag_gemm_inkernel()
+    torch.cuda.synchronize(); dist.barrier()
+    r = rel(cfull, refc)
+    same = torch.equal(buf.view(ag_off, (T, Kf), torch.bfloat16), torch.cat(gl))
+    good = r < 2e-2 and same
+    ok &= good; log(f"ag_gemm in-kernel push rel={r:.2e} gathered_equal={same} {'OK' if good else 'FAIL'}")
+    res["ag_gemm_inkernel"] = dict(T=T, K=Kf, N=Nf, fused_ms=timeit(run_ag_gemm_inkernel),
+                                   nccl_cublas_ms=timeit(ref_ag))
+    log(res["ag_gemm_inkernel"])
+except Exception as ex:
+    import traceback; traceback.print_exc(); ok = False; res["ag_gemm_inkernel_error"] = repr(ex)
+
 # ------------------------------------------------------------------ a2a rows
 hid, nrow = 1024, 4096
 src = torch.randn(nrow, hid, device=dev).to(torch.bfloat16)

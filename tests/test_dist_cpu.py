@@ -466,3 +466,25 @@ def _w_mixed_parallel_gpt(rank, world):
 
 def test_mixed_parallel_gpt_dp_pp_tp_zero():
     run_distributed(_w_mixed_parallel_gpt, 8)
+
+
+def _fd_share_worker(rank, world):
+    import os
+    import torch.distributed as dist
+    from torchdistpackage_b200.ops.symm import _share_fd
+    r, w = os.pipe()
+    os.write(w, f"rank{rank}".encode())
+    got = _share_fd(dist.group.WORLD, r, list(range(world)))
+    assert sorted(got) == [p for p in range(world) if p != rank]
+    dist.barrier()
+    # a pipe read end is shared, so each message is consumed exactly once: everyone reads from
+    # the pipe of the next rank only
+    nxt = (rank + 1) % world
+    assert os.read(got[nxt], 16) == f"rank{nxt}".encode()
+    only0 = _share_fd(dist.group.WORLD, r, [0])
+    assert (rank == 0 and only0 == {}) or (rank != 0 and list(only0) == [0])
+
+
+def test_symm_fd_passing():
+    """native symmetric-memory backend: POSIX fds travel between ranks with SCM_RIGHTS"""
+    run_distributed(_fd_share_worker, 3)

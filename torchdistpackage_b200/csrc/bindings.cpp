@@ -35,7 +35,7 @@ void check_bf16_2d(const Tensor& t, const char* name) {
 void gemm(const Tensor& a, const Tensor& b, Tensor& c, bool trans_a, bool trans_b,
           const OptTensor& bias, const OptTensor& residual, const OptTensor& aux_in,
           const OptTensor& aux_out, int64_t act, bool accumulate, double alpha, int64_t block_n,
-          int64_t max_ctas, int64_t split_k) {
+          int64_t max_ctas, int64_t split_k, int64_t cta_group) {
   check_bf16_2d(a, "a");
   check_bf16_2d(b, "b");
   TORCH_CHECK(c.is_cuda() && c.dim() == 2 && c.stride(1) == 1, "c must be a 2-D CUDA tensor");
@@ -82,6 +82,7 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& c, bool trans_a, bool trans_
   g.block_n = static_cast<int>(block_n);
   g.max_ctas = static_cast<int>(max_ctas);
   g.split_k = static_cast<int>(split_k);
+  g.cta_group = static_cast<int>(cta_group);
   const char* err = nullptr;
   count_launch();
   int rc = tdp::launch_gemm_bf16(g, cur_stream(), &err);
@@ -98,7 +99,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("trans_b") = false, py::arg("bias") = py::none(), py::arg("residual") = py::none(),
         py::arg("aux_in") = py::none(), py::arg("aux_out") = py::none(), py::arg("act") = 0,
         py::arg("accumulate") = false, py::arg("alpha") = 1.0, py::arg("block_n") = 0,
-        py::arg("max_ctas") = 0, py::arg("split_k") = 1);
+        py::arg("max_ctas") = 0, py::arg("split_k") = 1, py::arg("cta_group") = 0);
   m.def("num_sms", &tdp::gemm_num_sms);
   m.def("launch_count", []() { return g_launches.load(); });
   register_ext(m);

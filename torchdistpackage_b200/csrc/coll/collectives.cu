@@ -257,8 +257,12 @@ all_gather_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int w
 // (the fused all-gather->GEMM producer warp) poll flag[src] >= value on their own pad.
 // One counter per source rank is bumped once per *block*; consumer target = value * gridDim.x
 // is avoided by letting only the last block to finish (device-wide ticket) publish.
+// Runs CONCURRENTLY with the persistent GEMM that consumes it, and may be scheduled after that
+// GEMM already occupies every SM: the block must fit next to one GEMM CTA (10 warps x 144 regs,
+// 229.6 KB smem), hence 256 threads (16K regs) and ~1 KB of static smem.
+constexpr int kPushThreads = 256;
 template <bool kMc>
-__global__ void __launch_bounds__(kCollThreads)
+__global__ void __launch_bounds__(kPushThreads)
 all_gather_signal_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset,
                          size_t slice_vec, const uint4* src, size_t flag_word, uint32_t flag_value,
                          uint32_t* ticket) {
@@ -523,16 +527,17 @@ void launch_all_gather_signal(const SymmPeers& s, size_t offset, size_t slice_by
                               int use_mc, int max_ctas, cudaStream_t stream) {
   const size_t slice_vec = slice_bytes / 16;
   const bool mc = use_mc && s.mc_buf != nullptr;
-  const int blocks = pick_blocks(slice_vec, max_ctas);
+  // max_ctas is given in units of kCollThreads-wide CTAs; the push CTAs are half as wide
+  const int blocks = pick_blocks(slice_vec, max_ctas * (kCollThreads / kPushThreads));
   PeerPtrs pp = to_pp(s);
   char* mcp = reinterpret_cast<char*>(s.mc_buf);
   uint32_t* ticket = ticket_counter();
   if (mc)
-    all_gather_signal_kernel<true><<<blocks, kCollThreads, 0, stream>>>(
+    all_gather_signal_kernel<true><<<blocks, kPushThreads, 0, stream>>>(
         pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src),
         flag_word_offset, flag_value, ticket);
   else
-    all_gather_signal_kernel<false><<<blocks, kCollThreads, 0, stream>>>(
+    all_gather_signal_kernel<false><<<blocks, kPushThreads, 0, stream>>>(
         pp, mcp, s.rank, s.world, offset, slice_vec, reinterpret_cast<const uint4*>(src),
         flag_word_offset, flag_value, ticket);
 }

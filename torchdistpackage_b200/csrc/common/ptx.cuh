@@ -355,17 +355,18 @@ TDP_DEVICE float tanh_approx(float x) {
   return y;
 }
 TDP_DEVICE float gelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  const float u = k0 * x * (1.f + k1 * x * x);
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float u = x * fmaf(k01, x * x, k0);
   const float hx = 0.5f * x;
-  return hx + hx * tanh_approx(u);
+  return fmaf(hx, tanh_approx(u), hx);
 }
 TDP_DEVICE float dgelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
   const float x2 = x * x;
-  const float t = tanh_approx(k0 * x * (1.f + k1 * x2));
-  const float du = k0 * (1.f + 3.f * k1 * x2);
-  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+  const float t = tanh_approx(x * fmaf(k01, x2, k0));
+  const float du = fmaf(3.f * k01, x2, k0);
+  const float w = (0.5f * x) * fmaf(-t, t, 1.f);          // 0.5 x sech^2(u)
+  return fmaf(w, du, fmaf(0.5f, t, 0.5f));
 }
 TDP_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 TDP_DEVICE float dgelu_erf(float x) {

@@ -32,6 +32,7 @@ struct GemmLaunch {
   int act;               // GemmAct
   int split_k;           // >1: split K over CTAs (fp32 output, atomically accumulated)
   int block_n;           // 0 = auto, 128 or 256
+  int cta_group;         // 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (cta_group::2, 256x256)
   int max_ctas;          // 0 = all SMs (fused collectives reserve SMs for the comm CTAs)
   // fused collective hooks (see gemm_sm100.cuh)
   int comm_mode;
@@ -43,6 +44,12 @@ struct GemmLaunch {
   uint32_t flag_target;
   void* peer_out[kApiMaxPeers];
   uint32_t* peer_tile_counter[kApiMaxPeers];
+  // AG mode, push folded into the GEMM: a_local (contiguous) is copied by an extra warp of every
+  // CTA to push_dst[r] (+ my own slot) / push_mc, then push_flag[r] = flag_target is published
+  int push;
+  void* push_dst[kApiMaxPeers];
+  void* push_mc;
+  uint32_t* push_flag[kApiMaxPeers];
 };
 // returns 0 on success, otherwise a cudaError_t / negative code; `err` receives a message
 int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err);

@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
 #include "../common/tdp_api.h"
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_2cta.cuh"
 
 namespace tdp {
 
@@ -109,9 +111,39 @@ cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, kGemmThreads, S::kTotalBytes, stream>>>(
+  const int threads = p.push_src != nullptr ? kGemmThreadsPush : kGemmThreads;
+  gemm_bf16_sm100_kernel<BLOCK_N><<<grid, threads, S::kTotalBytes, stream>>>(
       ta, tb, ta_local, t_in, t_aux, sm, p);
   return cudaGetLastError();
+}
+
+template <int BLOCK_N>
+cudaError_t launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t_in,
+                        const CUtensorMap& t_aux, const CUtensorMap& tc, const GemmParams& p,
+                        int grid, cudaStream_t stream) {
+  using S = Gemm2CtaSmem<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_sm100_2cta_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotalBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_2cta_kernel<BLOCK_N>, ta, tb, t_in, t_aux, tc, p);
 }
 
 }  // namespace
@@ -217,6 +249,25 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     }
     p.has_a_local = 1;
   }
+  if (p.comm_mode == COMM_AG_WAIT_A && g.push) {
+    if (!p.has_a_local || g.lda_local != g.K || (static_cast<size_t>(g.rows_per_chunk) * g.K) % 8) {
+      snprintf(msg, sizeof(msg), "gemm(ag push): needs a contiguous local shard");
+      return -1;
+    }
+    static uint32_t* ticket = nullptr;      // one AG->GEMM at a time per process (it owns the GPU)
+    if (ticket == nullptr) {
+      if (cudaMalloc(&ticket, 64) != cudaSuccess) { snprintf(msg, sizeof(msg), "ticket alloc"); return -3; }
+      cudaMemset(ticket, 0, 64);
+    }
+    p.push_src = reinterpret_cast<const uint4*>(g.a_local);
+    p.push_vec = static_cast<size_t>(g.rows_per_chunk) * g.K * 2 / 16;
+    p.push_mc = reinterpret_cast<char*>(g.push_mc);
+    for (int r = 0; r < g.world; ++r) {
+      p.push_dst[r] = reinterpret_cast<char*>(g.push_dst[r]);
+      p.push_flag[r] = g.push_flag[r];
+    }
+    p.push_ticket = ticket;
+  }
 
   // output maps: bf16 results leave through swizzled smem + TMA store (128 x 64 boxes)
   GemmStoreMaps sm;
@@ -287,6 +338,34 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     p.k_blocks_per_split = static_cast<int>(share);
     grid = static_cast<int>((total + share - 1) / share);
   }
+  // 2-CTA (cta_group::2, 256 x 256 per CTA pair) path for plain bf16-output GEMMs
+  static const bool env_2cta = [] { const char* v = getenv("TDP_GEMM_2CTA"); return v && v[0] == '1'; }();
+  if ((g.cta_group == 2 || (g.cta_group == 0 && env_2cta)) && p.comm_mode == COMM_NONE &&
+      p.split_k == 1 && p.use_tma_store && g.N > 128 && g.M > 128) {
+    GemmParams q = p;
+    q.num_m_blocks = (g.M + 2 * kBlockM - 1) / (2 * kBlockM);
+    const int clusters = (max_ctas & ~1) / 2;
+    // pair tile 256 x 256, or 256 x 128 when the wide tiles cannot occupy every CTA pair
+    int bn2 = g.block_n == 128 ? 128 : 256;
+    if (g.block_n == 0 && static_cast<long>(q.num_m_blocks) * ((g.N + 255) / 256) < clusters) bn2 = 128;
+    q.num_n_blocks = (g.N + bn2 - 1) / bn2;
+    q.group_m = 4;
+    CUtensorMap tb2 = tb;
+    if (g.trans_b && !make_tmap_2d(&tb2, g.b, g.K, g.N, g.ldb, kBlockK, bn2 / 2)) {
+      snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(B, 2cta) failed");
+      return -2;
+    }
+    const long tiles2 = static_cast<long>(q.num_m_blocks) * q.num_n_blocks;
+    const int ctas = static_cast<int>(tiles2 < clusters ? tiles2 : clusters) * 2;
+    cudaError_t e2 = bn2 == 256 ? launch_2cta<256>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream)
+                                : launch_2cta<128>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream);
+    if (e2 != cudaSuccess) {
+      snprintf(msg, sizeof(msg), "gemm 2cta launch: %s", cudaGetErrorString(e2));
+      return static_cast<int>(e2);
+    }
+    return 0;
+  }
+
   cudaError_t e = (block_n == 256)
                       ? launch_impl<256>(ta, tb, ta_local, t_in, t_aux, sm, p, grid, stream)
                       : launch_impl<128>(ta, tb, ta_local, t_in, t_aux, sm, p, grid, stream);

@@ -24,6 +24,9 @@ constexpr int kUmmaK = 16;
 // latency and keeps up with the MMA pipe.
 constexpr int kNumEpilogueWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kNumEpilogueWarps);  // warp0 TMA, warp1 MMA, warps2-9 epi
+// all-gather->GEMM with the push folded in: one more warp per CTA copies this CTA's share of the
+// local shard to every peer while the tensor cores work on the chunks that are already there
+constexpr int kGemmThreadsPush = kGemmThreads + 32;
 constexpr int kMaxPeers = 8;
 constexpr int kStoreCols = 64;                         // TMA-store sub-tile: 128 rows x 64 cols
 constexpr int kStoreBytes = kBlockM * kStoreCols * 2;  // 16 KiB, 128B-swizzled
@@ -78,6 +81,13 @@ struct GemmParams {
   uint32_t* chunk_flags;          // [world] local flags (AG wait) -- device memory of this rank
   uint32_t flag_target;           // monotonically increasing epoch value
   uint32_t* peer_tile_counter[kMaxPeers];  // per-rank counter array [world(src)]
+  // in-kernel all-gather push (COMM_AG_WAIT_A, block of kGemmThreadsPush threads):
+  const uint4* push_src;          // this rank's shard (push_vec 16-byte vectors), null = no push
+  size_t push_vec;
+  char* push_dst[kMaxPeers];      // my slot in every rank's gather buffer (incl. my own)
+  char* push_mc;                  // multicast address of my slot (one store reaches all) or null
+  uint32_t* push_flag[kMaxPeers]; // chunk flag [my rank] in every rank's signal pad
+  uint32_t* push_ticket;          // local counter: the last CTA to finish publishes the flags
 };
 
 // C tensor maps: [0] = plain C; RS scatter: [d] = my slot in rank d's staging buffer
@@ -165,6 +175,30 @@ struct WorkIter {
 
 TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// v *= gelu'(z) for one thread-row x 32 columns; z comes from the TMA-loaded swizzled sub-tile
+// (`in_row`) or straight from global memory.
+template <bool kTanh>
+TDP_DEVICE void epilogue_dgelu(const GemmParams& p, float (&v)[32], int row, int col0, bool full,
+                               const uint8_t* in_row, int h, int swz) {
+  const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    if (full || col0 + j + 8 <= p.N) {
+      const uint4 z = (in_row != nullptr)
+          ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
+          : *reinterpret_cast<const uint4*>(zrow + j);
+      float zz[8];
+      float2 t;
+      t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
+      t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
+      t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
+      t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[j + q] *= kTanh ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
+    }
+  }
+}
+
 // Everything between the accumulator and the store for one thread-row x 32 columns.
 // `full` = the 32 columns are all inside N.
 // `in_row` (optional): this thread's row of the TMA-loaded, 128B-swizzled input sub-tile (residual
@@ -211,25 +245,11 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int 
   } else if (p.act == ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == ACT_DGELU_TANH || p.act == ACT_DGELU_ERF) {
-    const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (full || col0 + j + 8 <= p.N) {
-        const uint4 z = (in_row != nullptr)
-            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
-            : *reinterpret_cast<const uint4*>(zrow + j);
-        float zz[8];
-        float2 t;
-        t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
-        t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
-        t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
-        t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          v[j + q] *= (p.act == ACT_DGELU_TANH) ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
-      }
-    }
+  } else if (p.act == ACT_DGELU_TANH) {
+    // (one branch per flavour: a select inside the element loop makes ptxas evaluate both)
+    epilogue_dgelu<true>(p, v, row, col0, full, in_row, h, swz);
+  } else if (p.act == ACT_DGELU_ERF) {
+    epilogue_dgelu<false>(p, v, row, col0, full, in_row, h, swz);
   }
   if (p.residual != nullptr) {
     const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row) * p.ld_res + col0;
@@ -299,7 +319,7 @@ TDP_DEVICE void epilogue_store_direct(const GemmParams& p, float (&v)[32], uint8
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsPush, 1)
 gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_a_local,
@@ -448,7 +468,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         acc_phase ^= 1;
       }
     }
-  } else {
+  } else if (warp_idx < 2 + kNumEpilogueWarps) {
     // ================================ epilogue warps ================================
     // A warp may only touch TMEM lanes [32*(warp_idx%4), +32).
     const int quad = warp_idx & 3;
@@ -468,6 +488,13 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n0 = n_blk * BLOCK_N;
       const bool row_ok = row < p.M;
 
+      if (p.use_tma_store && p.epi_in_tma != 0 && issuer) {
+        // first row-wise input sub-tile of this tile: in flight while the MMAs still run
+        tma_store_wait_read<0>();                           // both staging buffers are free
+        mbar_expect_tx(&in_bar[store_buf], kStoreBytes);
+        tma_load_2d(&tmap_in, &in_bar[store_buf], smem_store + store_buf * kStoreBytes, n0,
+                    m_blk * kBlockM);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
@@ -490,12 +517,6 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool aux_tma = p.epi_aux_tma != 0;
         const int swz = row_in_tile & 7;
         const int n_sub = (min(BLOCK_N, p.N - n0) + kStoreCols - 1) / kStoreCols;
-        if (in_tma && issuer) {
-          tma_store_wait_read<0>();                         // both staging buffers are free
-          mbar_expect_tx(&in_bar[store_buf], kStoreBytes);
-          tma_load_2d(&tmap_in, &in_bar[store_buf], smem_store + store_buf * kStoreBytes, n0,
-                      m_blk * kBlockM);
-        }
 #pragma unroll 1
         for (int sub = 0; sub < n_sub; ++sub) {
           const int sc = sub * kStoreCols;
@@ -605,6 +626,50 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     // smem must stay valid until the last bulk stores have read it
     if (issuer) tma_store_wait<0>();
+  } else if (p.push_src != nullptr) {
+    // ================================ all-gather push warp ================================
+    // CTA b copies vectors {b*32 + lane + k*gridDim*32} of the local shard into slot `rank` of
+    // every rank's gather buffer (one multimem.st, or one st per peer).  Peers' producer warps
+    // wait on the chunk flag, which the last CTA to finish publishes -- the transfer overlaps the
+    // MMAs on the local chunk and needs no second kernel (no co-residency assumptions).
+    const int lane = threadIdx.x & 31;
+    const size_t stride = static_cast<size_t>(gridDim.x) * 32;
+    constexpr int kUnroll = 8;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * 32 + lane; i < p.push_vec;
+         i += stride * kUnroll) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t idx = i + u * stride;
+        if (idx < p.push_vec) v[u] = ld_nc_v4(p.push_src + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const size_t idx = i + u * stride;
+        if (idx < p.push_vec) {
+          if (p.push_mc != nullptr) {
+            multimem_st_v4(p.push_mc + idx * 16, v[u]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+              if (r < p.world) st_na_v4(p.push_dst[r] + idx * 16, v[u]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) {
+      fence_acq_rel_sys();                       // my stores happen-before the ticket
+      const uint32_t t = atomicAdd(p.push_ticket, 1u);
+      fence_acq_rel_sys();                       // the other CTAs' stores happen-before the flags
+      last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      if (lane < p.world) st_release_sys(p.push_flag[lane], p.flag_target);
+      if (lane == 0) *p.push_ticket = 0u;
+    }
   }
 
   tc_fence_before();

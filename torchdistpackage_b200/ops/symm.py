@@ -32,24 +32,55 @@ def _dtype_code(dtype: torch.dtype) -> int:
     raise TypeError(f"symmetric collectives support bf16 / fp32, got {dtype}")
 
 
-def _pidfd_getfd(pid: int, fd: int) -> int:
-    """Duplicate file descriptor ``fd`` of process ``pid`` into this process (Linux >= 5.6)."""
-    import ctypes
+_fd_serial = [0]
+
+
+def _share_fd(pg, fd, owners):
+    """Hand POSIX file descriptors to the other ranks of ``pg`` (same node) over abstract-namespace
+    unix sockets with SCM_RIGHTS.  Every rank in ``owners`` serves its ``fd`` to all other ranks;
+    returns ``{owner_rank: local duplicate}`` for the owners other than this rank.  (pidfd_getfd
+    would be simpler but needs ptrace rights that containers usually drop.)"""
     import os
-    pidfd = os.pidfd_open(pid)
-    try:
-        libc = ctypes.CDLL(None, use_errno=True)
-        new = libc.syscall(438, pidfd, fd, 0)       # __NR_pidfd_getfd (x86_64 / aarch64)
-        if new < 0:
-            raise OSError(ctypes.get_errno(), "pidfd_getfd failed")
-        return int(new)
-    finally:
-        os.close(pidfd)
+    import socket
+    import threading
+    rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+    _fd_serial[0] += 1
+    addr = f"\0tdp-symm-{os.getpid()}-{_fd_serial[0]}"
+    srv = None
+    if rank in owners:
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(addr)
+        srv.listen(world)
+    addrs = [None] * world
+    dist.all_gather_object(addrs, addr if srv is not None else None, group=pg)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            with conn:
+                socket.send_fds(conn, [b"f"], [fd])
+
+    th = None
+    if srv is not None:
+        th = threading.Thread(target=serve, daemon=True)
+        th.start()
+    got = {}
+    for r in owners:
+        if r == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+            c.connect(addrs[r])
+            _, fds, _, _ = socket.recv_fds(c, 16, 1)
+            got[r] = fds[0]
+    if th is not None:
+        th.join()
+        srv.close()
+    return got
 
 
 def _native_symm_alloc(pg, nbytes: int, want_multicast: bool):
     """Our own symmetric allocation (csrc/symm/symm_vmm.cpp): VMM allocation exported as a POSIX
-    fd, fds exchanged with ``pidfd_getfd`` over the process group, every peer's memory mapped
+    fd, fds passed between the ranks over unix sockets (SCM_RIGHTS), every peer's memory mapped
     here, one multicast object bound to all of them.  Layout: [data | 64 KiB signal pad].
     Returns ``(tensor, buffer_ptrs, signal_ptrs, multicast_ptr)``."""
     import os
@@ -60,33 +91,36 @@ def _native_symm_alloc(pg, nbytes: int, want_multicast: bool):
     data = (nbytes + 4095) // 4096 * 4096
     total = (data + SIGNAL_PAD_BYTES + gran - 1) // gran * gran
     h, ptr, fd = C.vmm_alloc(total, dev)
-    infos = [None] * world
-    dist.all_gather_object(infos, (os.getpid(), fd), group=pg)
+    peer_fds = _share_fd(pg, fd, list(range(world)))
     ptrs = []
-    for r, (pid, pfd) in enumerate(infos):
+    for r in range(world):
         if r == rank:
             ptrs.append(ptr)
         else:
-            dup = _pidfd_getfd(pid, pfd)
-            _, pp = C.vmm_import(dup, total, dev)
-            os.close(dup)
+            _, pp = C.vmm_import(peer_fds[r], total, dev)
+            os.close(peer_fds[r])
             ptrs.append(pp)
     mc_ptr = 0
     if want_multicast:
-        ok = 1
-        try:
-            if rank == 0:
+        ok, mch, mcfd = 1, None, -1
+        if rank == 0:
+            try:
                 mch, mcfd = C.mc_create(total, world)
-                box = [(os.getpid(), mcfd)]
-            else:
-                box = [None]
-            dist.broadcast_object_list(box, src=dist.get_global_rank(pg, 0), group=pg)
+            except Exception:       # pragma: no cover - depends on driver / fabric support
+                ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)      # did rank 0 get its object?
+        want_multicast = int(flag.item()) == 1
+    if want_multicast:
+        try:
+            got = _share_fd(pg, mcfd, [0])
             if rank != 0:
-                dup = _pidfd_getfd(box[0][0], box[0][1])
-                mch = C.mc_import(dup)
-                os.close(dup)
+                mch = C.mc_import(got[0])
+                os.close(got[0])
+            else:
+                os.close(mcfd)
             C.mc_add_device(mch, dev)
-        except Exception:           # pragma: no cover - depends on driver / fabric support
+        except Exception:           # pragma: no cover
             ok = 0
         flag = torch.tensor([ok], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)      # everyone added its device

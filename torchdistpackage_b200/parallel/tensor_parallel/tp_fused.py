@@ -27,6 +27,8 @@ attn.py:93-98, mlp.py:69-78), which run back to back on one stream.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -36,7 +38,8 @@ from ...ops import linear as L
 from ...ops._loader import native
 from ...ops.symm import SymmBuffer, get_symm_group
 
-_AG_PUSH_CTAS = 24      # SMs worth of push CTAs (co-resident with the persistent GEMM)
+_AG_PUSH_CTAS = 16      # side-stream push variant: SMs left free by the GEMM for the push CTAs
+_AG_PUSH_IN_KERNEL = os.environ.get("TDP_AG_PUSH", "kernel") != "side"
 _ENABLED = True
 
 
@@ -113,17 +116,23 @@ def _ag_gemm(ctx: FusedSpContext, name: str, x_shard: torch.Tensor, w: torch.Ten
     buf = reg.buf
     out = torch.empty(T, N, dtype=torch.bfloat16, device=x_shard.device)
     aux_out = torch.empty(T, N, dtype=torch.bfloat16, device=x_shard.device) if want_aux_out else None
-    cur = torch.cuda.current_stream()
     off = reg.next_offset()                  # ping-pong half: no barrier needed (see _Region)
     ep = buf.next_epoch(reg.flag_word)
-    ctx.side.wait_stream(cur)
-    with torch.cuda.stream(ctx.side):
-        buf.handle.all_gather_signal(off, rows * K * 2, x_shard, reg.flag_word, ep, True,
-                                     _AG_PUSH_CTAS)
-    x_shard.record_stream(ctx.side)
-    buf.handle.gemm_ag(off, rows, K, w, trans_b, out, bias, aux_out, act, reg.flag_word, ep, 0,
-                       x_shard, aux_in)
-    cur.wait_stream(ctx.side)
+    if _AG_PUSH_IN_KERNEL and x_shard.is_contiguous():
+        # one kernel: an extra warp of every GEMM CTA pushes its share of the local shard to all
+        # peers (multimem.st) while the tensor cores start on the local chunk
+        buf.handle.gemm_ag(off, rows, K, w, trans_b, out, bias, aux_out, act, reg.flag_word, ep,
+                           0, x_shard, aux_in, True, True)
+    else:
+        cur = torch.cuda.current_stream()
+        ctx.side.wait_stream(cur)
+        with torch.cuda.stream(ctx.side):
+            buf.handle.all_gather_signal(off, rows * K * 2, x_shard, reg.flag_word, ep, True,
+                                         _AG_PUSH_CTAS)
+        x_shard.record_stream(ctx.side)
+        buf.handle.gemm_ag(off, rows, K, w, trans_b, out, bias, aux_out, act, reg.flag_word, ep,
+                           L._num_sms() - _AG_PUSH_CTAS, x_shard, aux_in)
+        cur.wait_stream(ctx.side)
     gathered = buf.view(off, (T, K), torch.bfloat16)
     gathered._tdp_token = (reg, ep)          # lets backward detect that the buffer was re-used
     return out, gathered, aux_out
