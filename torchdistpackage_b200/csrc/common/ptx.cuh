@@ -368,6 +368,63 @@ TDP_DEVICE float dgelu_tanh(float x) {
   const float w = (0.5f * x) * fmaf(-t, t, 1.f);          // 0.5 x sech^2(u)
   return fmaf(w, du, fmaf(0.5f, t, 0.5f));
 }
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 do two fp32 lanes per issue slot).
+// The GEMM epilogues are issue-bound, so the element-wise math runs on register pairs.
+using f32x2 = unsigned long long;
+TDP_DEVICE f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+TDP_DEVICE void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+TDP_DEVICE f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+TDP_DEVICE f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+TDP_DEVICE f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+TDP_DEVICE f32x2 splat2(float x) { return pk2(x, x); }
+// bf16x2 word -> two fp32 lanes (a shift and a mask)
+TDP_DEVICE f32x2 bf16x2_to_f32x2(uint32_t u) {
+  return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+TDP_DEVICE uint32_t f32x2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+TDP_DEVICE f32x2 tanh_approx2(f32x2 u) {
+  float a, b;
+  upk2(u, a, b);
+  return pk2(tanh_approx(a), tanh_approx(b));
+}
+TDP_DEVICE f32x2 gelu_tanh2(f32x2 x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 u = mul2(x, fma2(splat2(k01), mul2(x, x), splat2(k0)));
+  const f32x2 hx = mul2(x, splat2(0.5f));
+  return fma2(hx, tanh_approx2(u), hx);
+}
+// returns g * gelu'(x)
+TDP_DEVICE f32x2 dgelu_tanh2(f32x2 x, f32x2 g) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x2 = mul2(x, x);
+  const f32x2 t = tanh_approx2(mul2(x, fma2(splat2(k01), x2, splat2(k0))));
+  const f32x2 du = fma2(splat2(3.f * k01), x2, splat2(k0));
+  const f32x2 sech = fma2(mul2(t, splat2(-1.f)), t, splat2(1.f));
+  const f32x2 w = mul2(mul2(x, splat2(0.5f)), sech);                 // 0.5 x sech^2(u)
+  return mul2(g, fma2(w, du, fma2(splat2(0.5f), t, splat2(0.5f))));
+}
 TDP_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 TDP_DEVICE float dgelu_erf(float x) {
   float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));

@@ -339,8 +339,13 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     grid = static_cast<int>((total + share - 1) / share);
   }
   // 2-CTA (cta_group::2, 256 x 256 per CTA pair) path for plain bf16-output GEMMs
-  static const bool env_2cta = [] { const char* v = getenv("TDP_GEMM_2CTA"); return v && v[0] == '1'; }();
-  if ((g.cta_group == 2 || (g.cta_group == 0 && env_2cta)) && p.comm_mode == COMM_NONE &&
+  // auto (cta_group == 0): CTA pairs pay off when the main loop dominates (long K: B is fetched
+  // once per pair, 6 smem stages) -- measured on B200: +8..12 % at K >= 2304, neutral at K = 768,
+  // slower with the heavy GELU epilogues.  TDP_GEMM_2CTA=0/1 forces the choice.
+  static const int env_2cta = [] { const char* v = getenv("TDP_GEMM_2CTA"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
+  bool auto_2cta = g.K >= 2048 && g.act == ACT_NONE && g.aux_out == nullptr;
+  if (env_2cta >= 0) auto_2cta = env_2cta == 1;
+  if ((g.cta_group == 2 || (g.cta_group == 0 && auto_2cta)) && p.comm_mode == COMM_NONE &&
       p.split_k == 1 && p.use_tma_store && g.N > 128 && g.M > 128) {
     GemmParams q = p;
     q.num_m_blocks = (g.M + 2 * kBlockM - 1) / (2 * kBlockM);

@@ -175,47 +175,24 @@ struct WorkIter {
 
 TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// v *= gelu'(z) for one thread-row x 32 columns; z comes from the TMA-loaded swizzled sub-tile
-// (`in_row`) or straight from global memory.
-template <bool kTanh>
-TDP_DEVICE void epilogue_dgelu(const GemmParams& p, float (&v)[32], int row, int col0, bool full,
-                               const uint8_t* in_row, int h, int swz) {
-  const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    if (full || col0 + j + 8 <= p.N) {
-      const uint4 z = (in_row != nullptr)
-          ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
-          : *reinterpret_cast<const uint4*>(zrow + j);
-      float zz[8];
-      float2 t;
-      t = unpack_bf16x2(z.x); zz[0] = t.x; zz[1] = t.y;
-      t = unpack_bf16x2(z.y); zz[2] = t.x; zz[3] = t.y;
-      t = unpack_bf16x2(z.z); zz[4] = t.x; zz[5] = t.y;
-      t = unpack_bf16x2(z.w); zz[6] = t.x; zz[7] = t.y;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[j + q] *= kTanh ? dgelu_tanh(zz[q]) : dgelu_erf(zz[q]);
-    }
-  }
-}
-
-// Everything between the accumulator and the store for one thread-row x 32 columns.
+// Everything between the accumulator and the store for one thread-row x 32 columns, on packed
+// fp32x2 lanes: v[i] holds columns (2i, 2i+1).
 // `full` = the 32 columns are all inside N.
 // `in_row` (optional): this thread's row of the TMA-loaded, 128B-swizzled input sub-tile (residual
 // or dGELU pre-activation) -- chunk c of the 64-column sub-tile lives at (c ^ swz) * 16.
 // `z_row` (optional): same layout, receives the pre-activation copy instead of a global store.
-TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int col0, bool full,
+TDP_DEVICE void epilogue_math(const GemmParams& p, f32x2 (&v)[16], int row, int col0, bool full,
                               const uint8_t* in_row = nullptr, uint8_t* z_row = nullptr, int h = 0,
                               int swz = 0) {
   if (p.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (full || col0 + j + 8 <= p.N) {
-        const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + j);
-        const float2 b0 = unpack_bf16x2(b.x), b1 = unpack_bf16x2(b.y), b2 = unpack_bf16x2(b.z),
-                     b3 = unpack_bf16x2(b.w);
-        v[j] += b0.x; v[j + 1] += b0.y; v[j + 2] += b1.x; v[j + 3] += b1.y;
-        v[j + 4] += b2.x; v[j + 5] += b2.y; v[j + 6] += b3.x; v[j + 7] += b3.y;
+    for (int j = 0; j < 4; ++j) {
+      if (full || col0 + 8 * j + 8 <= p.N) {
+        const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + 8 * j);
+        v[4 * j] = add2(v[4 * j], bf16x2_to_f32x2(b.x));
+        v[4 * j + 1] = add2(v[4 * j + 1], bf16x2_to_f32x2(b.y));
+        v[4 * j + 2] = add2(v[4 * j + 2], bf16x2_to_f32x2(b.z));
+        v[4 * j + 3] = add2(v[4 * j + 3], bf16x2_to_f32x2(b.w));
       }
     }
   }
@@ -223,55 +200,92 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, float (&v)[32], int row, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 o;
-      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      o.x = f32x2_to_bf16x2(v[4 * j]); o.y = f32x2_to_bf16x2(v[4 * j + 1]);
+      o.z = f32x2_to_bf16x2(v[4 * j + 2]); o.w = f32x2_to_bf16x2(v[4 * j + 3]);
       *reinterpret_cast<uint4*>(z_row + (((h * 4 + j) ^ swz) * 16)) = o;
     }
   } else if (p.aux_out != nullptr) {
     __nv_bfloat16* arow = p.aux_out + static_cast<size_t>(row) * p.ld_aux + col0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (full || col0 + j + 8 <= p.N) {
+    for (int j = 0; j < 4; ++j) {
+      if (full || col0 + 8 * j + 8 <= p.N) {
         uint4 o;
-        o.x = pack_bf16x2(v[j], v[j + 1]); o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        o.z = pack_bf16x2(v[j + 4], v[j + 5]); o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(arow + j) = o;
+        o.x = f32x2_to_bf16x2(v[4 * j]); o.y = f32x2_to_bf16x2(v[4 * j + 1]);
+        o.z = f32x2_to_bf16x2(v[4 * j + 2]); o.w = f32x2_to_bf16x2(v[4 * j + 3]);
+        *reinterpret_cast<uint4*>(arow + 8 * j) = o;
       }
     }
   }
+  // (one branch per activation flavour: a select inside the element loop makes ptxas evaluate both)
   if (p.act == ACT_GELU_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+    for (int i = 0; i < 16; ++i) v[i] = gelu_tanh2(v[i]);
   } else if (p.act == ACT_GELU_ERF) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == ACT_DGELU_TANH) {
-    // (one branch per flavour: a select inside the element loop makes ptxas evaluate both)
-    epilogue_dgelu<true>(p, v, row, col0, full, in_row, h, swz);
-  } else if (p.act == ACT_DGELU_ERF) {
-    epilogue_dgelu<false>(p, v, row, col0, full, in_row, h, swz);
+    for (int i = 0; i < 16; ++i) {
+      float a, b;
+      upk2(v[i], a, b);
+      v[i] = pk2(gelu_erf(a), gelu_erf(b));
+    }
+  } else if (p.act == ACT_DGELU_TANH || p.act == ACT_DGELU_ERF) {
+    const __nv_bfloat16* zrow = p.aux_in + static_cast<size_t>(row) * p.ld_aux + col0;
+    const bool tanh_flavour = p.act == ACT_DGELU_TANH;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (full || col0 + 8 * j + 8 <= p.N) {
+        const uint4 z = (in_row != nullptr)
+            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j) ^ swz) * 16))
+            : *reinterpret_cast<const uint4*>(zrow + 8 * j);
+        const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+        if (tanh_flavour) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[4 * j + q] = dgelu_tanh2(bf16x2_to_f32x2(zw[q]), v[4 * j + q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float z0, z1, g0, g1;
+            upk2(bf16x2_to_f32x2(zw[q]), z0, z1);
+            upk2(v[4 * j + q], g0, g1);
+            v[4 * j + q] = pk2(g0 * dgelu_erf(z0), g1 * dgelu_erf(z1));
+          }
+        }
+      }
+    }
   }
   if (p.residual != nullptr) {
     const __nv_bfloat16* rrow = p.residual + static_cast<size_t>(row) * p.ld_res + col0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (full || col0 + j + 8 <= p.N) {
+    for (int j = 0; j < 4; ++j) {
+      if (full || col0 + 8 * j + 8 <= p.N) {
         const uint4 z = (in_row != nullptr)
-            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j / 8) ^ swz) * 16))
-            : *reinterpret_cast<const uint4*>(rrow + j);
-        float2 t;
-        t = unpack_bf16x2(z.x); v[j] += t.x; v[j + 1] += t.y;
-        t = unpack_bf16x2(z.y); v[j + 2] += t.x; v[j + 3] += t.y;
-        t = unpack_bf16x2(z.z); v[j + 4] += t.x; v[j + 5] += t.y;
-        t = unpack_bf16x2(z.w); v[j + 6] += t.x; v[j + 7] += t.y;
+            ? *reinterpret_cast<const uint4*>(in_row + (((h * 4 + j) ^ swz) * 16))
+            : *reinterpret_cast<const uint4*>(rrow + 8 * j);
+        v[4 * j] = add2(v[4 * j], bf16x2_to_f32x2(z.x));
+        v[4 * j + 1] = add2(v[4 * j + 1], bf16x2_to_f32x2(z.y));
+        v[4 * j + 2] = add2(v[4 * j + 2], bf16x2_to_f32x2(z.z));
+        v[4 * j + 3] = add2(v[4 * j + 3], bf16x2_to_f32x2(z.w));
       }
     }
   }
 }
 
+// accumulator registers (fp32 bit patterns from tcgen05.ld) -> packed lanes, scaled by alpha
+TDP_DEVICE void epilogue_load_acc(const GemmParams& p, const uint32_t (&r)[32], f32x2 (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = pk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+  if (p.alpha != 1.f) {
+    const f32x2 a2 = splat2(p.alpha);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = mul2(v[i], a2);
+  }
+}
+
 // direct (row-per-thread) global store, used for fp32 output / accumulate
-TDP_DEVICE void epilogue_store_direct(const GemmParams& p, float (&v)[32], uint8_t* c_row,
+TDP_DEVICE void epilogue_store_direct(const GemmParams& p, const f32x2 (&v2)[16], uint8_t* c_row,
                                       int col0, bool full) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) upk2(v2[i], v[2 * i], v[2 * i + 1]);
   if (p.c_fp32) {
     float* crow = reinterpret_cast<float*>(c_row) + col0;
     if (p.split_k > 1) {
@@ -549,9 +563,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tmem_ld_32x32b_x32(taddr + sc + h * 32, r);
             tmem_ld_wait();
             const int col0 = n0 + sc + h * 32;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            f32x2 v[16];
+            epilogue_load_acc(p, r, v);
             if (row_ok && col0 < p.N)
               epilogue_math(p, v, row, col0, col0 + 32 <= p.N, in_tma ? srow : nullptr,
                             aux_tma ? srow : nullptr, h, swz);
@@ -560,10 +573,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
-              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              o.x = f32x2_to_bf16x2(v[4 * j]);
+              o.y = f32x2_to_bf16x2(v[4 * j + 1]);
+              o.z = f32x2_to_bf16x2(v[4 * j + 2]);
+              o.w = f32x2_to_bf16x2(v[4 * j + 3]);
               *reinterpret_cast<uint4*>(wrow + (((h * 4 + j) ^ swz) * 16)) = o;
             }
           }
@@ -607,9 +620,8 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_wait();
           const int col0 = n0 + c;
           if (row_ok && col0 < p.N) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            f32x2 v[16];
+            epilogue_load_acc(p, r, v);
             const bool full = (col0 + 32 <= p.N);
             epilogue_math(p, v, row, col0, full);
             epilogue_store_direct(p, v, c_row, col0, full);

@@ -284,9 +284,8 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tmem_ld_32x32b_x32(taddr + sc + h * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + sc + h * 32;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          f32x2 v[16];
+          epilogue_load_acc(p, r, v);
           if (row_ok && col0 < p.N)
             epilogue_math(p, v, row, col0, col0 + 32 <= p.N, in_tma ? srow : nullptr,
                           aux_tma ? srow : nullptr, h, swz);
@@ -294,10 +293,10 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-            o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            o.x = f32x2_to_bf16x2(v[4 * j]);
+            o.y = f32x2_to_bf16x2(v[4 * j + 1]);
+            o.z = f32x2_to_bf16x2(v[4 * j + 2]);
+            o.w = f32x2_to_bf16x2(v[4 * j + 3]);
             *reinterpret_cast<uint4*>(wrow + (((h * 4 + j) ^ swz) * 16)) = o;
           }
         }

@@ -14,6 +14,7 @@ of the fc2 dgrad GEMM (``ACT_DGELU``).  bf16 CUDA tensors take the native path; 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -58,11 +59,21 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
              and act == ACT_NONE and not accumulate and out is None
              and (out_dtype in (None, torch.bfloat16)))
     if split_k == 0 and plain:
-        # stream-K whenever the 128x256 output tiles cannot fill the machine for >= ~3 waves and K
-        # is long enough to amortise the fp32 atomics (weight gradients: K = tokens)
+        # weight-gradient shapes (few output tiles, K = tokens).  If 256x128 CTA-pair tiles give
+        # one reasonably full wave, the 2-CTA kernel writes bf16 directly (no fp32 scratch, no
+        # cast); stream-K only when the 128x256 tiles cannot fill even one wave and K is long enough
+        # to amortise the fp32 atomics; everything else goes to the plain kernels (the launcher
+        # picks CTA pairs for K >= 2048).
         sms = _num_sms()
         tiles = -(-M // 128) * -(-N // 256)
-        if tiles < 3 * sms and K >= 2048 and tiles % sms != 0:
+        pair_tiles = -(-M // 256) * -(-N // 128)
+        if K >= 2048 and M > 128 and N > 128 and 0.6 * (sms // 2) <= pair_tiles <= sms // 2 \
+                and _WGRAD_2CTA:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+            C.gemm(a, b, out, trans_a, trans_b, None, None, None, None, 0, False, float(alpha),
+                   128, int(max_ctas), 1, 2)
+            return out
+        if tiles < sms and K >= 2048:
             split_k = 2
     if split_k > 1 and plain:
         acc = torch.zeros(M, N, dtype=torch.float32, device=a.device)
@@ -79,6 +90,7 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
 
 
 _SMS = None
+_WGRAD_2CTA = os.environ.get("TDP_WGRAD_2CTA", "1") == "1"
 
 
 def _num_sms() -> int:
