@@ -107,9 +107,23 @@ else:
         k = tgt.shape[0] // 2
         logits = stage.head(stage.ln_f(x))
         return F.cross_entropy(logits.view(-1, V), tgt[tp_rank * k:(tp_rank + 1) * k].reshape(-1)) / 2
-    opt = pkg.Bf16ZeroOptimizer(torch.optim.AdamW(stage.parameters(), lr=1e-4), dp_group=dpg)
-    post_backward = lambda: None
+    note = ""
+    if args.micro > 1:
+        # The reference's Bf16ZeroOptimizer frees p.grad inside its backward hook, so a second
+        # micro-batch crashes in copy2master_or_free (zero_optim.py:222, 'NoneType'.data): ZeRO +
+        # gradient accumulation is unsupported there.  Its arm therefore runs the reference's
+        # NaiveDDP(num_grad_acc_iter) + a plain (fused) AdamW -- less communication than ZeRO.
+        # (hooks sit on the parameters, so fwd_fn keeps calling the bare stage modules)
+        ddp_stage = pkg.NaiveDDP(stage, sync=False, process_group=dpg,
+                                 num_grad_acc_iter=args.micro) if dp > 1 else None
+        opt = torch.optim.AdamW(stage.parameters(), lr=1e-4, fused=True)
+        post_backward = (lambda: ddp_stage.reduce_gradients()) if dp > 1 else (lambda: None)
+        note = " [reference arm: NaiveDDP + AdamW, its ZeRO cannot accumulate gradients]"
+    else:
+        opt = pkg.Bf16ZeroOptimizer(torch.optim.AdamW(stage.parameters(), lr=1e-4), dp_group=dpg)
+        post_backward = lambda: None
 
+note = globals().get("note", "")
 gen = torch.Generator().manual_seed(100 + pkg.tpc.get_group_rank("data"))
 tok = torch.randint(0, V, (args.batch, S + 1), generator=gen).to(dev)
 tokens, targets = tok[:, :-1].contiguous(), tok[:, 1:].contiguous()
@@ -138,7 +152,8 @@ lossv = torch.tensor([float(out.detach().float().item()) * 2 if last else 0.0], 
 dist.all_reduce(lossv, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"config": f"GPT-2 {args.model} DP={dp} x PP=2 x TP=2 (+SP), ZeRO over data, 1F1B, "
-                                f"{args.micro} micro-batches, batch {args.batch}/replica, seq {S}",
+                                f"{args.micro} micro-batches, batch {args.batch}/replica, seq {S}"
+                                + (note if args.impl == "reference" else ""),
                       "impl": args.impl, "n_gpus": world, "ms_per_step": t.item(),
                       "tokens_per_s": dp * args.batch * S / (t.item() / 1e3), "dtype": "bf16",
                       "loss": lossv.item()}), flush=True)

@@ -165,6 +165,8 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
                           cudaStream_t stream);
 void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols, void* out,
                                   int out_bf16, cudaStream_t stream);
+void launch_colsum_partial_reduce2(const float* partial, int n_partial, int cols, void* out0,
+                                   void* out1, int out_bf16, cudaStream_t stream);
 // column sum of bf16 [rows, cols] (bias gradient)
 void launch_colsum(const void* x, int rows, int cols, int ld, float* scratch, void* out,
                    int out_bf16, cudaStream_t stream);

@@ -345,8 +345,11 @@ layernorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
 constexpr int kCsRows = 64;
 __global__ void __launch_bounds__(256)
 colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int ld,
-                     float* __restrict__ out /* zero-initialised fp32 [cols] */) {
+                     float* __restrict__ scratch /* persistent fp32 [cols], all zero on entry */,
+                     unsigned int* __restrict__ tickets /* one per column group, zero on entry */,
+                     void* __restrict__ out, int out_bf16) {
   __shared__ float sred[8][256];
+  __shared__ unsigned int s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x / 32;
   const int col = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * kCsRows;
@@ -364,12 +367,27 @@ colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, in
 #pragma unroll
   for (int k = 0; k < 8; ++k) sred[w][lane * 8 + k] = acc[k];
   __syncthreads();
-  const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < cols) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) t += sred[ww][c];
-    atomicAdd(out + blockIdx.x * 256 + c, t);
+    for (int ww = 0; ww < 8; ++ww) t += sred[ww][threadIdx.x];
+    atomicAdd(scratch + c, t);
+  }
+  // the last block of this column group converts the sums and leaves scratch / ticket zeroed for
+  // the next call: one launch per bias gradient, no memset, no second kernel
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (c < cols) {
+      const float t = atomicExch(scratch + c, 0.f);
+      if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[c] = __float2bfloat16_rn(t);
+      else reinterpret_cast<float*>(out)[c] = t;
+    }
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
   }
 }
 
@@ -377,10 +395,14 @@ colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, in
 // (coalesced 128-byte rows), then the 8 warp sums meet in shared memory.
 __global__ void __launch_bounds__(256)
 colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int cols,
-                             void* __restrict__ out, int out_bf16) {
+                             void* __restrict__ out, int out_bf16, size_t partial_stride_y,
+                             void* __restrict__ out_y1) {
+  // blockIdx.y selects an independent problem (LayerNorm: 0 = dgamma, 1 = dbeta)
   __shared__ float sred[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + lane;
+  partial += blockIdx.y * partial_stride_y;
+  if (blockIdx.y == 1) out = out_y1;
   float acc = 0.f;
   if (c < cols) {
 #pragma unroll 4
@@ -535,17 +557,39 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
 void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols, void* out,
                                   int out_bf16, cudaStream_t stream) {
   colsum_partial_reduce_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partial, n_partial, cols, out,
-                                                                    out_bf16);
+                                                                    out_bf16, 0, nullptr);
 }
 
-void launch_colsum(const void* x, int rows, int cols, int ld, float* scratch, void* out,
-                   int out_bf16, cudaStream_t stream) {
-  // scratch: >= cols fp32 (caller allocates); zeroed here, filled with atomics, then cast
-  cudaMemsetAsync(scratch, 0, sizeof(float) * cols, stream);
-  dim3 grid((cols + 255) / 256, (rows + kCsRows - 1) / kCsRows);
-  colsum_atomic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows,
-                                                 cols, ld, scratch);
-  launch_colsum_partial_reduce(scratch, 1, cols, out, out_bf16, stream);
+void launch_colsum_partial_reduce2(const float* partial, int n_partial, int cols, void* out0,
+                                   void* out1, int out_bf16, cudaStream_t stream) {
+  // partial = [2][n_partial][cols]; one launch reduces both halves
+  dim3 grid((cols + 31) / 32, 2);
+  colsum_partial_reduce_kernel<<<grid, 256, 0, stream>>>(
+      partial, n_partial, cols, out0, out_bf16, static_cast<size_t>(n_partial) * cols, out1);
+}
+
+void launch_colsum(const void* x, int rows, int cols, int ld, float* /*scratch (unused)*/,
+                   void* out, int out_bf16, cudaStream_t stream) {
+  // persistent self-cleaning accumulators (per device): zero before and after every call
+  constexpr int kMaxCols = 1 << 18;
+  static float* acc[16] = {nullptr};
+  static unsigned int* tick[16] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (acc[dev] == nullptr) {
+    cudaMalloc(&acc[dev], sizeof(float) * kMaxCols);
+    cudaMemset(acc[dev], 0, sizeof(float) * kMaxCols);
+    cudaMalloc(&tick[dev], sizeof(unsigned int) * (kMaxCols / 256));
+    cudaMemset(tick[dev], 0, sizeof(unsigned int) * (kMaxCols / 256));
+  }
+  for (int c0 = 0; c0 < cols; c0 += kMaxCols) {
+    const int nc = cols - c0 < kMaxCols ? cols - c0 : kMaxCols;
+    dim3 grid((nc + 255) / 256, (rows + kCsRows - 1) / kCsRows);
+    colsum_atomic_kernel<<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x) + c0, rows, nc, ld, acc[dev], tick[dev],
+        static_cast<char*>(out) + static_cast<size_t>(c0) * (out_bf16 ? 2 : 4), out_bf16);
+  }
 }
 
 void launch_cross_entropy_fwd_bwd(void* logits, int rows, int vocab, int ld, const int64_t* target,

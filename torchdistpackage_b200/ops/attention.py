@@ -30,8 +30,13 @@ class _PackedAttnFn(torch.autograd.Function):
         with torch.enable_grad():
             q, k, v = (qkv5[:, :, i].transpose(1, 2).detach().requires_grad_(True) for i in range(3))
             o = F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale)
-        out = torch.empty(B, T, n_head, dh, dtype=qkv.dtype, device=qkv.device)
-        C.permute_rows_copy(out.transpose(1, 2), o)
+        ot = o.transpose(1, 2)
+        if ot.is_contiguous():
+            # the library laid O out like Q (physically [B, T, H, Dh]): already what we return
+            out = ot.detach()
+        else:
+            out = torch.empty(B, T, n_head, dh, dtype=qkv.dtype, device=qkv.device)
+            C.permute_rows_copy(out.transpose(1, 2), o)
         ctx.graph = (q, k, v, o)
         ctx.dims = (B, T, n_head, dh)
         return out.view(B, T, D)
@@ -42,8 +47,12 @@ class _PackedAttnFn(torch.autograd.Function):
         B, T, H, dh = ctx.dims
         q, k, v, o = ctx.graph
         ctx.graph = None
-        do = torch.empty(B, H, T, dh, dtype=dout.dtype, device=dout.device)
-        C.permute_rows_copy(do, dout.reshape(B, T, H, dh).transpose(1, 2))
+        dview = dout.reshape(B, T, H, dh).transpose(1, 2)
+        if dview.stride() == o.stride():
+            do = dview                      # dO already has O's physical layout: no permute
+        else:
+            do = torch.empty(B, H, T, dh, dtype=dout.dtype, device=dout.device)
+            C.permute_rows_copy(do, dview)
         dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
         dqkv = torch.empty(B, T, 3, H, dh, dtype=dout.dtype, device=dout.device)
         for i, g in enumerate((dq, dk, dv)):
