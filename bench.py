@@ -210,8 +210,29 @@ def build_ours(args, device, world):
     return counted_step, launches, model.cfg
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """stdout must carry exactly ONE JSON line.  Native libraries (NCCL prints its version banner
+    with printf) write to fd 1 directly, so fd 1 is pointed at stderr for the whole run and the
+    JSON line is written to a saved duplicate of the real stdout."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT_FD if _REAL_STDOUT_FD is not None else 1, line)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -222,7 +243,7 @@ def main():
             import ref_bench
         except Exception as e:  # reference not installed / importable on this box
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}))
+                emit_json({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"})
             return
         builder = ref_bench.build_reference
     else:
@@ -231,7 +252,7 @@ def main():
     if not torch.cuda.is_available():
         if args.impl == "reference":
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "no CUDA device"}))
+                emit_json({"impl": "reference", "unavailable": "no CUDA device"})
             return
         raise SystemExit("bench.py needs a CUDA device (B200)")
 
@@ -343,7 +364,7 @@ def main():
             "final_loss": final_loss,
             "model_flops_utilization_of_measured_cublas": mfu,
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

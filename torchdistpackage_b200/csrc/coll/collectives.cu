@@ -55,6 +55,11 @@ __device__ __forceinline__ void wait_signal(uint32_t* addr) {
 //   pad[slot_base + blockIdx.x * world + src_rank]
 __device__ __forceinline__ void block_barrier(const PeerPtrs& pp, int rank, int world,
                                               int slot_base) {
+  // every thread drains its own peer / multimem stores to system scope before the block's
+  // signalling threads publish: the release of the signalling thread alone is not relied upon
+  // to cover the other threads' in-flight multicast stores (8-GPU fan-out is slow enough for a
+  // peer to overwrite -- e.g. zero -- a slot and then receive a late store on top of it).
+  __threadfence_system();
   __syncthreads();
   if (threadIdx.x < world) {
     const int peer = threadIdx.x;
@@ -291,6 +296,7 @@ all_gather_signal_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank
       }
     }
   }
+  __threadfence_system();      // each thread's own peer / multicast stores reach system scope
   __syncthreads();
   __shared__ uint32_t s_last;
   if (threadIdx.x == 0) {

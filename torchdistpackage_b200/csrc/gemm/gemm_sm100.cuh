@@ -669,6 +669,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
+    fence_acq_rel_sys();                         // every lane drains its own multicast stores
     __syncwarp();
     uint32_t last = 0;
     if (lane == 0) {

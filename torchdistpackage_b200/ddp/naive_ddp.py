@@ -203,6 +203,11 @@ class _GradReducer:
                     if p.grad is not None:
                         view.copy_(p.grad)
                     p.grad = view
+                    if self.on_cuda and p.dim() == 2 and p.dtype == torch.bfloat16:
+                        # lets ops.linear.wgrad write the weight gradient straight into the bucket
+                        p._tdp_main_grad = view
+                        p._tdp_grad_fresh = True
+                        p._tdp_on_grad_ready = self._make_direct_ready(name, p)
             self.buckets.append(bucket)
 
     # ------------------------------------------------------------------ hooks
@@ -217,10 +222,19 @@ class _GradReducer:
             self._on_grad_ready(name, p)
         return hook
 
+    def _make_direct_ready(self, name: str, p: torch.nn.Parameter):
+        def ready():
+            self._on_grad_ready(name, p)
+        return ready
+
     def remove_hooks(self) -> None:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for p in self.params.values():
+            for attr in ("_tdp_main_grad", "_tdp_grad_fresh", "_tdp_on_grad_ready"):
+                if hasattr(p, attr):
+                    delattr(p, attr)
 
     def _on_grad_ready(self, name: str, p: torch.Tensor) -> None:
         bucket = self.param_bucket[name]
@@ -319,6 +333,9 @@ class _GradReducer:
             bucket.grad_reset()
         self._acc_counter.clear()
         self._finalized = True
+        for p in self.params.values():      # next backward overwrites instead of accumulating
+            if hasattr(p, "_tdp_grad_fresh"):
+                p._tdp_grad_fresh = True
         if self.verbose:
             self.reduce_time += time.perf_counter() - t0
             print(f"[NaiveDDP] rank {dist.get_rank() if dist.is_initialized() else 0}: "
@@ -429,7 +446,12 @@ class NaiveDDP(torch.nn.Module):
                 if set_to_none:
                     p.grad = None
                 else:
-                    p.grad.detach_()
+                    # (bucket views cannot be detach_()ed in place -- same rule as torch's
+                    # Optimizer.zero_grad)
+                    if p.grad.grad_fn is not None:
+                        p.grad.detach_()
+                    else:
+                        p.grad.requires_grad_(False)
                     p.grad.zero_()
 
 

@@ -110,6 +110,8 @@ class GPT2(nn.Module):
         self.blocks = nn.ModuleList([GPT2Block(cfg) for _ in range(cfg.n_layer)])
         self.ln_f = nn.LayerNorm(cfg.d_model)
         nn.init.normal_(self.wte.weight, std=0.02)
+        # tied with the LM head: two gradient contributions per step, autograd must sum them
+        self.wte.weight._tdp_no_fused_wgrad = True
         nn.init.normal_(self.wpe.weight, std=0.02)
 
     def embed(self, idx: torch.Tensor) -> torch.Tensor:

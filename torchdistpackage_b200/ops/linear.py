@@ -56,8 +56,9 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
     K = a.shape[0] if trans_a else a.shape[1]
     C = native(required=True)
     plain = (bias is None and residual is None and aux_in is None and aux_out is None
-             and act == ACT_NONE and not accumulate and out is None
-             and (out_dtype in (None, torch.bfloat16)))
+             and act == ACT_NONE and not accumulate
+             and (out_dtype in (None, torch.bfloat16))
+             and (out is None or (out.dtype == torch.bfloat16 and out.is_contiguous())))
     if split_k == 0 and plain:
         # weight-gradient shapes (few output tiles, K = tokens).  If 256x128 CTA-pair tiles give
         # one reasonably full wave, the 2-CTA kernel writes bf16 directly (no fp32 scratch, no
@@ -69,7 +70,8 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
         pair_tiles = -(-M // 256) * -(-N // 128)
         if K >= 2048 and M > 128 and N > 128 and 0.6 * (sms // 2) <= pair_tiles <= sms // 2 \
                 and _WGRAD_2CTA:
-            out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+            if out is None:
+                out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
             C.gemm(a, b, out, trans_a, trans_b, None, None, None, None, 0, False, float(alpha),
                    128, int(max_ctas), 1, 2)
             return out
@@ -79,7 +81,8 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
         acc = torch.zeros(M, N, dtype=torch.float32, device=a.device)
         C.gemm(a, b, acc, trans_a, trans_b, None, None, None, None, 0, False, float(alpha),
                256 if N > 128 else 128, int(max_ctas), int(split_k))
-        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        if out is None:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
         C.cast_copy(out.view(-1), acc.view(-1), 1.0)
         return out
     if out is None:
@@ -91,6 +94,7 @@ def gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=N
 
 _SMS = None
 _WGRAD_2CTA = os.environ.get("TDP_WGRAD_2CTA", "1") == "1"
+_FUSED_WGRAD = os.environ.get("TDP_FUSED_WGRAD", "1") == "1"
 
 
 def _num_sms() -> int:
@@ -107,6 +111,27 @@ def colsum(x2d: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
     else:
         out.copy_(x2d.float().sum(0))
     return out
+
+
+def wgrad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
+    """Weight gradient ``a^T @ b`` for parameter ``w``.
+
+    If ``w.grad`` is a view of a gradient bucket that a reducer (NaiveDDP) registered on the
+    parameter (``w._tdp_main_grad``), the GEMM epilogue writes the bucket directly -- overwriting on
+    the first micro-step after a reduction, accumulating afterwards -- the reducer is told the
+    gradient is final, and ``None`` is returned to autograd: no temporary, no ``grad += dw``
+    kernel per parameter.  Otherwise returns the gradient tensor for autograd to accumulate."""
+    buf = getattr(w, "_tdp_main_grad", None)
+    if buf is None or w.grad is None or w.grad.data_ptr() != buf.data_ptr() \
+            or getattr(w, "_tdp_no_fused_wgrad", False) or not _FUSED_WGRAD:
+        return gemm(a, b, trans_a=True)
+    if w._tdp_grad_fresh:
+        gemm(a, b, trans_a=True, out=buf)
+        w._tdp_grad_fresh = False
+    else:
+        gemm(a, b, trans_a=True, out=buf, accumulate=True)
+    w._tdp_on_grad_ready()
+    return None
 
 
 def _act_ref(z, act):
@@ -151,9 +176,9 @@ class _LinearFn(torch.autograd.Function):
             dx = gemm(dz, w, trans_b=not ctx.layout_nk).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
             if ctx.layout_nk:   # dW [N, K] = dz^T @ x
-                dw = gemm(dz, x2, trans_a=True)
+                dw = wgrad(w, dz, x2)
             else:               # dW [K, N] = x^T @ dz
-                dw = gemm(x2, dz, trans_a=True)
+                dw = wgrad(w, x2, dz)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dz)
         if ctx.has_res and ctx.needs_input_grad[5]:
@@ -204,10 +229,10 @@ class _MlpFn(torch.autograd.Function):
         has_b1, has_b2, has_res = ctx.flags
         # dz = (dy @ W2^T) * act'(z)   -- derivative applied in the epilogue
         dz = gemm(dy2, w2, trans_b=not nk, act=_DACT[ctx.act], aux_in=z)
-        dw2 = gemm(dy2, a, trans_a=True) if nk else gemm(a, dy2, trans_a=True)
+        dw2 = wgrad(w2, dy2, a) if nk else wgrad(w2, a, dy2)
         db2 = colsum(dy2) if has_b2 else None
         dx = gemm(dz, w1, trans_b=not nk).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
-        dw1 = gemm(dz, x2, trans_a=True) if nk else gemm(x2, dz, trans_a=True)
+        dw1 = wgrad(w1, dz, x2) if nk else wgrad(w1, x2, dz)
         db1 = colsum(dz) if has_b1 else None
         dres = dy if has_res else None
         return dx, dw1, db1, dw2, db2, None, None, dres
