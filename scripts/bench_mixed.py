@@ -114,8 +114,8 @@ else:
         # gradient accumulation is unsupported there.  Its arm therefore runs the reference's
         # NaiveDDP(num_grad_acc_iter) + a plain (fused) AdamW -- less communication than ZeRO.
         # (hooks sit on the parameters, so fwd_fn keeps calling the bare stage modules)
-        ddp_stage = pkg.NaiveDDP(stage, sync=False, process_group=dpg,
-                                 num_grad_acc_iter=args.micro) if dp > 1 else None
+        ddp_stage = pkg.NaiveDDP(stage, sync=False, process_group=dpg, num_grad_acc_iter=args.micro,
+                                 dp_rank0=pkg.tpc.get_ranks_in_group("data")[0]) if dp > 1 else None
         opt = torch.optim.AdamW(stage.parameters(), lr=1e-4, fused=True)
         post_backward = (lambda: ddp_stage.reduce_gradients()) if dp > 1 else (lambda: None)
         note = " [reference arm: NaiveDDP + AdamW, its ZeRO cannot accumulate gradients]"

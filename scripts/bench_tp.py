@@ -55,6 +55,8 @@ with torch.no_grad():           # same sane init in every arm (the reference use
             p.copy_(torch.randn(p.shape, generator=g) * 0.02)
 model = model.to(dev).to(torch.bfloat16)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+if args.batch % world:      # sequence parallelism shards dim 0 of [B, N, h]
+    args.batch = -(-args.batch // world) * world
 x = torch.randn(args.batch, args.seq, args.dim, device=dev).to(torch.bfloat16)
 dist.broadcast(x, 0)
 

@@ -44,10 +44,13 @@ for it in range(2):
         if p.grad is not None: p.grad.zero_()
     loss = ddp(tok[:, :-1], tok[:, 1:]); loss.backward(); ddp.reduce_gradients()
 ref(tok[:, :-1], tok[:, 1:]).backward()
-worst = 0.0
+worst, worst_name = 0.0, ""
 for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
     g = q.grad.float().clone(); dist.all_reduce(g); g /= world
-    worst = max(worst, rel(p.grad, g))
+    r_ = rel(p.grad, g)
+    if r_ > worst: worst, worst_name = r_, n
+    if r_ > 3e-2: log(f"  ddp grad mismatch {n}: rel {r_:.3e} |ref|max {g.abs().max().item():.3e}")
+res["ddp_worst_param"] = worst_name
 check("ddp_grad_vs_nccl_avg", worst, 3e-2)
 
 # BucketAdamW vs torch AdamW (fp32 master) for 3 steps on the averaged grads
@@ -112,7 +115,8 @@ for it in range(10):
         for p in em.parameters(): p.add_(torch.randn_like(p) * 0.1)
     ema.update(em, decay=0.9)
     for n, p in em.named_parameters(): full[n].mul_(0.9).add_(p.detach().float(), alpha=0.1)
-check("sharded_ema_vs_full", max(rel(t, full[n]) for n, t in ema.state_dict_shard().items()), 3e-2)
+# (with more ranks than parameters a rank may own nothing)
+check("sharded_ema_vs_full", max((rel(t, full[n]) for n, t in ema.state_dict_shard().items()), default=0.0), 3e-2)
 sdc = ema.state_dict_cpu()
 ok &= (sdc is not None) == (rank == 0)
 

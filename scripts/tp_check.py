@@ -106,9 +106,10 @@ def step_time(fused, dim=4096, heads=32, depth=4, B=4, N=2048, iters=6, warm=3):
     torch.cuda.empty_cache()
     return t.item()
 try:
-    if B % world == 0:
-        t_f = step_time(True); t_n = step_time(False)
-        res["tp_transformer_ms"] = dict(fused=t_f, nccl=t_n, tokens=4 * 2048)
+    if True:
+        Bt = max(4, world)          # sequence parallelism shards dim 0: needs B % tp == 0
+        t_f = step_time(True, B=Bt); t_n = step_time(False, B=Bt)
+        res["tp_transformer_ms"] = dict(fused=t_f, nccl=t_n, tokens=Bt * 2048)
         log("transformer fwd+bwd ms: fused", t_f, "nccl", t_n)
 except Exception as ex:
     import traceback; traceback.print_exc(); res["timing_error"] = repr(ex)
