@@ -177,11 +177,6 @@ void launch_cross_entropy_fwd_bwd(void* logits, int rows, int vocab, int ld, con
                                   float* loss, float grad_scale, int ignore_index,
                                   cudaStream_t stream);
 
-// causal / bidirectional flash attention, bf16, head_dim 64 or 128, layout [B, S, H, D]
-void launch_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
-                           int B, int S, int H, int D, int q_stride, int kv_stride, int o_stride,
-                           int causal, float scale, cudaStream_t stream);
-
 // ------------------------------------------------------------------ native symmetric memory
 // (symm/symm_vmm.cpp): CUDA VMM allocations exported as POSIX fds, peer mapping, NVLS multicast
 bool vmm_granularity(int device, int num_devices, uint64_t* gran, std::string& err);
