@@ -263,3 +263,59 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
             assert q.grad.data_ptr() == red.param_bucket[n].views[n].data_ptr(), n
             assert torch.allclose(q.grad.float(), p.grad.float(), rtol=2e-2, atol=1e-3), n
         assert all(p._tdp_grad_fresh for p in wrapped.parameters() if hasattr(p, "_tdp_grad_fresh"))
+
+
+def test_step_watchdog_fires_and_recovers():
+    import io
+    import time
+    from torchdistpackage_b200.tools import StepWatchdog
+    hangs = []
+    buf = io.StringIO()
+    wd = StepWatchdog(timeout_s=0.3, poll_s=0.05, on_hang=hangs.append, stream=buf, rank=0, world=1)
+    with wd:
+        for s in range(3):                  # healthy: ticks faster than the timeout
+            wd.tick(s)
+            time.sleep(0.05)
+        assert hangs == []
+        time.sleep(0.6)                     # "hang"
+        assert len(hangs) == 1 and hangs[0]["last_step"] == 2 and hangs[0]["idle_s"] >= 0.3
+        time.sleep(0.3)
+        assert len(hangs) == 1              # reported once per stall
+        wd.tick(3)                          # progress re-arms it
+        time.sleep(0.6)
+        assert len(hangs) == 2 and hangs[1]["last_step"] == 3
+    assert "no training step" in buf.getvalue() and "Thread" in buf.getvalue()
+
+
+def test_metrics_logger_jsonl(tmp_path):
+    import json
+    from torchdistpackage_b200.tools import MetricsLogger
+    path = tmp_path / "m" / "train.jsonl"
+    with MetricsLogger(str(path), rank=0) as m:
+        m.log(1, loss=torch.tensor(2.5), tokens_per_s=1e6, tag="warmup", lr=[1e-3, 1e-4])
+        m.log(2, loss=2.25)
+    rows = [json.loads(l) for l in open(path)]
+    assert [r["step"] for r in rows] == [1, 2]
+    assert rows[0]["loss"] == 2.5 and rows[0]["tag"] == "warmup" and rows[0]["lr"] == [1e-3, 1e-4]
+    silent = MetricsLogger(str(tmp_path / "other.jsonl"), rank=3)      # non-zero rank: no file
+    silent.log(1, loss=1.0)
+    assert not (tmp_path / "other.jsonl").exists()
+
+
+def test_async_checkpoint_writer_roundtrip(tmp_path):
+    from torchdistpackage_b200.dist.model_parallel_ckpt import AsyncCheckpointWriter, load_mp_checkpoint
+    w = AsyncCheckpointWriter()
+    model_state = {"w": torch.arange(12.).view(3, 4), "nested": {"b": torch.ones(2)}, "step": 7}
+    shard = {"exp_avg": [torch.zeros(3), torch.full((2,), 0.5)]}
+    prefix = str(tmp_path / "ck" / "it7")
+    w.save(prefix, model_state, shard)
+    model_state["w"].add_(100)              # mutate after save(): the snapshot must not change
+    w.wait()
+    state, sh = load_mp_checkpoint(prefix, with_shard=True)
+    assert torch.equal(state["w"], torch.arange(12.).view(3, 4)) and state["step"] == 7
+    assert torch.equal(state["nested"]["b"], torch.ones(2))
+    assert torch.equal(sh["exp_avg"][1], torch.full((2,), 0.5))
+    assert not any(p.name.endswith(".tmp") for p in (tmp_path / "ck").iterdir())
+    w.save(str(tmp_path / "no" / "\0bad"), {"x": torch.ones(1)})        # unwritable path
+    with pytest.raises(RuntimeError):
+        w.wait()

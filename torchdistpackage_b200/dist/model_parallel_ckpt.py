@@ -55,3 +55,80 @@ def load_mp_checkpoint(prefix: str, map_location="cpu", with_shard: bool = False
     shard = torch.load(prefix + "_shard" + get_mp_ckpt_suffix(include_dp=True),
                        map_location=map_location, weights_only=False)
     return state, shard
+
+
+class AsyncCheckpointWriter:
+    """Checkpoint without stalling the training loop.
+
+    ``save(prefix, model_state, sharded_state)`` copies every tensor to (pinned, when CUDA is
+    present) host memory on a side stream, records an event and returns; a background thread waits
+    for the event and does the ``torch.save`` file I/O with the same naming / writer rules as
+    :func:`save_mp_checkpoint`.  One save is in flight at a time (a second ``save`` first waits for
+    the previous one), ``wait()`` blocks until the files are on disk, ``last_error`` keeps a
+    failure of the background write.  Files are written to ``<name>.tmp`` and renamed, so a job
+    killed mid-write never leaves a truncated checkpoint behind."""
+
+    def __init__(self):
+        import threading
+        self._thread: Optional["threading.Thread"] = None
+        self._stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.last_error: Optional[BaseException] = None
+        self.last_paths: list = []
+
+    def _to_host(self, obj):
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda:
+                host = torch.empty(obj.shape, dtype=obj.dtype, device="cpu", pin_memory=True)
+                host.copy_(obj, non_blocking=True)
+                return host
+            return obj.detach().clone()
+        if isinstance(obj, dict):
+            return type(obj)((k, self._to_host(v)) for k, v in obj.items())
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._to_host(v) for v in obj)
+        return obj
+
+    def save(self, prefix: str, model_state: Dict[str, Any],
+             sharded_state: Optional[Dict[str, Any]] = None) -> None:
+        import threading
+        self.wait()
+        os.makedirs(os.path.dirname(os.path.abspath(prefix)) or ".", exist_ok=True)
+        jobs = []
+        event = None
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            ctx = torch.cuda.stream(self._stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if _is_dp_writer():
+                jobs.append((prefix + get_mp_ckpt_suffix(), self._to_host(model_state)))
+            if sharded_state is not None:
+                jobs.append((prefix + "_shard" + get_mp_ckpt_suffix(include_dp=True),
+                             self._to_host(sharded_state)))
+            if self._stream is not None:
+                event = torch.cuda.Event()
+                event.record(self._stream)
+
+        def write():
+            try:
+                if event is not None:
+                    event.synchronize()
+                for path, state in jobs:
+                    torch.save(state, path + ".tmp")
+                    os.replace(path + ".tmp", path)
+                self.last_paths = [p for p, _ in jobs]
+            except BaseException as e:      # surfaced by wait()
+                self.last_error = e
+
+        self._thread = threading.Thread(target=write, name="tdp-async-ckpt", daemon=True)
+        self._thread.start()
+
+    def wait(self) -> None:
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        if self.last_error is not None:
+            err, self.last_error = self.last_error, None
+            raise RuntimeError("asynchronous checkpoint write failed") from err

@@ -2,3 +2,5 @@ from .module_profiler import register_profile_hooks, report_prof, get_model_prof
 from .module_replace import replace_all_module
 from .debug_nan import (check_tensors, check_model_params, fwd_hook_wrapper, bwd_hook_wrapper,
                         register_nan_hooks)
+from .watchdog import StepWatchdog, HANG_EXIT_CODE
+from .metrics import MetricsLogger
