@@ -177,6 +177,23 @@ void launch_cross_entropy_fwd_bwd(void* logits, int rows, int vocab, int ld, con
                                   float* loss, float grad_scale, int ignore_index,
                                   cudaStream_t stream);
 
+// ------------------------------------------------------------------ attention (attn/*.cu)
+// Flash-attention forward, bf16, head_dim 64.  q / k / v / o are token matrices: row b*T + t,
+// row stride ld_* elements, head h at columns [h*D, (h+1)*D) from the given base pointer (so q, k
+// and v may be three column windows of one packed qkv projection).  lse: fp32 [B, H, T] or null.
+struct AttnFwdLaunch {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  float* lse;
+  int B, T, H, D;
+  int ld_q, ld_k, ld_v, ld_o;
+  int causal;
+  float scale;
+};
+int launch_attn_fwd(const AttnFwdLaunch& a, cudaStream_t stream, const char** err);
+
 // ------------------------------------------------------------------ native symmetric memory
 // (symm/symm_vmm.cpp): CUDA VMM allocations exported as POSIX fds, peer mapping, NVLS multicast
 bool vmm_granularity(int device, int num_devices, uint64_t* gran, std::string& err);

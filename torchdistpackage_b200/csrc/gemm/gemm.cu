@@ -10,6 +10,7 @@
 #include <unordered_map>
 
 #include "../common/tdp_api.h"
+#include "../common/tmap.h"
 #include "gemm_sm100.cuh"
 #include "gemm_sm100_2cta.cuh"
 
@@ -49,6 +50,9 @@ struct TmapKeyHash {
 };
 
 // bf16 2-D row-major view [outer, inner] with leading dimension ld (elements), 128B swizzle.
+}  // namespace
+
+// (declared in common/tmap.h: shared with the attention kernels)
 bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                   uint32_t box_inner, uint32_t box_outer) {
   static std::mutex mu;
@@ -95,6 +99,8 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
   cache.emplace(key, *out);
   return true;
 }
+
+namespace {
 
 int g_num_sms = 0;
 

@@ -1,7 +1,9 @@
 """Attention over a packed qkv projection without layout round trips.
 
-The attention core itself is the library flash kernel (``scaled_dot_product_attention``: cuDNN's
-sm_100 kernel on B200) -- see DESIGN.md for the status of a tcgen05 attention kernel.  What is
+The attention core used for training is the library flash kernel (``scaled_dot_product_attention``:
+cuDNN's sm_100 kernel on B200).  The package's own tcgen05 forward kernel
+(``native_attention_forward``) exists but is opt-in (``TDP_ATTN=native``, no-grad calls only) until
+it has been validated on hardware and has a backward -- see DESIGN.md.  What is
 ours is everything around it: q / k / v are strided *views* of the packed ``[B, T, 3*H*Dh]`` GEMM
 output (no split copies), the ``[B,H,T,Dh] -> [B,T,H*Dh]`` output permute and, in backward, the
 ``dO`` permute and the scatter of dq / dk / dv into ONE packed ``[B, T, 3*H*Dh]`` gradient are
@@ -62,12 +64,43 @@ class _PackedAttnFn(torch.autograd.Function):
         return dqkv.view(B, T, 3 * H * dh), None, None, None
 
 
+def native_attention_forward(qkv: torch.Tensor, n_head: int, causal: bool = True,
+                             scale: Optional[float] = None, return_lse: bool = False):
+    """Forward-only attention on the package's own tcgen05 kernel (csrc/attn/attn_fwd_sm100.cu):
+    q, k, v are read in place from the packed projection, the output is written in ``[B, T, H*Dh]``
+    layout, no layout copies at all.  head_dim 64, ``T % 128 == 0``.  No autograd (a backward
+    kernel does not exist yet): used for evaluation / inference when ``TDP_ATTN=native``."""
+    C = native(required=True)
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    dh = D // n_head
+    qkv5 = qkv.detach().view(B, T, 3, n_head, dh)
+    out = torch.empty(B, T, n_head, dh, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B, n_head, T, dtype=torch.float32, device=qkv.device) if return_lse else None
+    C.attn_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], out, lse, bool(causal),
+               float(scale if scale is not None else dh ** -0.5))
+    out = out.view(B, T, D)
+    return (out, lse) if return_lse else out
+
+
+def _use_native_attention(qkv: torch.Tensor, n_head: int) -> bool:
+    import os
+    if os.environ.get("TDP_ATTN", "library") != "native":
+        return False
+    B, T, D3 = qkv.shape
+    dh = D3 // 3 // n_head
+    return (not (torch.is_grad_enabled() and qkv.requires_grad)) and dh == 64 and T % 128 == 0 \
+        and qkv.dtype == torch.bfloat16 and hasattr(native(), "attn_fwd")
+
+
 def packed_attention(qkv: torch.Tensor, n_head: int, causal: bool = True,
                      scale: Optional[float] = None) -> torch.Tensor:
     """``qkv`` ``[B, T, 3*H*Dh]`` (q | k | v along the last dim) -> ``[B, T, H*Dh]``."""
     B, T, D3 = qkv.shape
     D = D3 // 3
     dh = D // n_head
+    if native() is not None and qkv.is_cuda and qkv.is_contiguous() and _use_native_attention(qkv, n_head):
+        return native_attention_forward(qkv, n_head, causal, scale)
     if native() is not None and qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16) \
             and (dh * qkv.element_size()) % 16 == 0 and qkv.is_contiguous():
         return _PackedAttnFn.apply(qkv, n_head, causal, scale)
