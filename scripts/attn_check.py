@@ -51,6 +51,35 @@ for (B, T, H, causal) in [(1, 128, 1, False), (1, 128, 1, True), (2, 256, 2, Tru
         break
 
 
+# ---- backward: dqkv of the native kernels vs autograd through the fp32 reference
+os.environ["TDP_ATTN"] = "native"
+from torchdistpackage_b200.ops.attention import packed_attention  # noqa: E402
+if ok:
+    for (B, T, H, causal) in [(1, 128, 1, False), (1, 256, 1, True), (2, 384, 2, True), (2, 512, 4, False),
+                              (2, 1024, 12, True)]:
+        qkv = (torch.randn(B, T, 3 * H * 64, device=dev) * 0.7).to(torch.bfloat16).requires_grad_(True)
+        dout = (torch.randn(B, T, H * 64, device=dev) * 0.5).to(torch.bfloat16)
+        try:
+            out = packed_attention(qkv, H, causal)
+            out.backward(dout)
+            torch.cuda.synchronize()
+            qr = qkv.detach().float().requires_grad_(True)
+            ro, _ = ref_attn(qr, H, causal)
+            ro.backward(dout.float())
+            g, gr = qkv.grad.float().view(B, T, 3, H, 64), qr.grad.view(B, T, 3, H, 64)
+            errs = [((g[:, :, i] - gr[:, :, i]).abs().max() / gr[:, :, i].abs().max()).item() for i in range(3)]
+            good = max(errs) < 3e-2
+        except Exception as ex:
+            errs = [float("nan")] * 3; good = False
+            print("ERROR", repr(ex), flush=True)
+        ok &= good
+        rec = dict(bwd=True, B=B, T=T, H=H, causal=causal, dq_rel=errs[0], dk_rel=errs[1], dv_rel=errs[2], ok=good)
+        res["numerics"].append(rec)
+        print(rec, flush=True)
+        if not good:
+            break
+
+
 def timeit(fn, iters=20, warm=5):
     for _ in range(warm):
         fn()
@@ -75,6 +104,23 @@ if ok:
                    library_tflops=fl / t_lib / 1e9, native_tflops=fl / t_own / 1e9)
         res["timing"].append(rec)
         print(rec, flush=True)
+        # forward + backward
+        qg = qkv.clone().requires_grad_(True)
+        q4, k4, v4 = (t.detach().requires_grad_(True) for t in (q, k, v))
+        dout = torch.randn(B, T, H * 64, device=dev).to(torch.bfloat16)
+        do_lib = dout.view(B, T, H, 64).transpose(1, 2)
+
+        def lib_step():
+            o = F.scaled_dot_product_attention(q4, k4, v4, is_causal=causal)
+            torch.autograd.grad(o, (q4, k4, v4), do_lib)
+
+        def own_step():
+            o = packed_attention(qg, H, causal)
+            torch.autograd.grad(o, qg, dout)
+        rec2 = dict(B=B, T=T, H=H, causal=causal, fwd_bwd=True, library_ms=timeit(lib_step),
+                    native_ms=timeit(own_step))
+        res["timing"].append(rec2)
+        print(rec2, flush=True)
 res["all_ok"] = bool(ok)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/attn_check.json", "w"), indent=1)

@@ -80,7 +80,7 @@ TDP_DEVICE void wg_bar_sync(int wg) {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 128}
                       const __grid_constant__ CUtensorMap tmap_k,   // box {64, 128}
-                      const __grid_constant__ CUtensorMap tmap_v,   // box {64, 64}
+                      const __grid_constant__ CUtensorMap tmap_v,   // box {64, 128}
                       const __grid_constant__ CUtensorMap tmap_o,   // box {64, 128}
                       const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -156,11 +156,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
                     row_base + j * kTileKV);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], kTileBytes);
-        // V tile as two [64 keys x 64 d] boxes: the MN-major B operand of P.V, one box per k-block
+        // one [128 keys x 64 d] box: rows of 128 B, i.e. two stacked [64 x 64] boxes -- exactly the
+        // MN-major B operand of P.V (one 8 KiB box per 64-key k-block)
         tma_load_2d(&tmap_v, &v_full[st], smem_v + st * kTileBytes, p.v_col0 + h * kHeadDim,
                     row_base + j * kTileKV);
-        tma_load_2d(&tmap_v, &v_full[st], smem_v + st * kTileBytes + kTileBytes / 2,
-                    p.v_col0 + h * kHeadDim, row_base + j * kTileKV + 64);
       }
     }
   } else if (warp_idx == 1) {
@@ -376,7 +375,7 @@ int launch_attn_fwd(const AttnFwdLaunch& a, cudaStream_t stream, const char** er
   const uint64_t width = static_cast<uint64_t>(a.H) * a.D;
   if (!make_tmap_2d(&tq, a.q, width, rows, a.ld_q, 64, kTileQ) ||
       !make_tmap_2d(&tk, a.k, width, rows, a.ld_k, 64, kTileKV) ||
-      !make_tmap_2d(&tv, a.v, width, rows, a.ld_v, 64, 64) ||
+      !make_tmap_2d(&tv, a.v, width, rows, a.ld_v, 64, kTileKV) ||
       !make_tmap_2d(&to, a.o, width, rows, a.ld_o, 64, kTileQ)) {
     snprintf(msg, sizeof(msg), "attn_fwd: cuTensorMapEncodeTiled failed");
     return -2;

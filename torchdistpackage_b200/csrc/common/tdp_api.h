@@ -194,6 +194,26 @@ struct AttnFwdLaunch {
 };
 int launch_attn_fwd(const AttnFwdLaunch& a, cudaStream_t stream, const char** err);
 
+// Flash-attention backward (same token-matrix contract).  lse: forward's [B, H, T]; delta:
+// rowsum(dO * O) as fp32 [B, H, T]; dq_acc: zero-initialised fp32 [B*T, H*D] accumulator (query
+// gradients of different key tiles are added with red.global); dk / dv: bf16 token matrices.
+struct AttnBwdLaunch {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* d_o;
+  const float* lse;
+  const float* delta;
+  float* dq_acc;
+  void* dk;
+  void* dv;
+  int B, T, H, D;
+  int ld_q, ld_k, ld_v, ld_do, ld_dk, ld_dv;
+  int causal;
+  float scale;
+};
+int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** err);
+
 // ------------------------------------------------------------------ native symmetric memory
 // (symm/symm_vmm.cpp): CUDA VMM allocations exported as POSIX fds, peer mapping, NVLS multicast
 bool vmm_granularity(int device, int num_devices, uint64_t* gran, std::string& err);

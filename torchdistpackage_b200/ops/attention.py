@@ -1,9 +1,9 @@
 """Attention over a packed qkv projection without layout round trips.
 
 The attention core used for training is the library flash kernel (``scaled_dot_product_attention``:
-cuDNN's sm_100 kernel on B200).  The package's own tcgen05 forward kernel
-(``native_attention_forward``) exists but is opt-in (``TDP_ATTN=native``, no-grad calls only) until
-it has been validated on hardware and has a backward -- see DESIGN.md.  What is
+cuDNN's sm_100 kernel on B200).  The package's own tcgen05 forward / backward kernels
+(csrc/attn, ``_NativeAttnFn``) exist but stay opt-in (``TDP_ATTN=native``) until they have been
+validated on hardware -- see DESIGN.md.  What is
 ours is everything around it: q / k / v are strided *views* of the packed ``[B, T, 3*H*Dh]`` GEMM
 output (no split copies), the ``[B,H,T,Dh] -> [B,T,H*Dh]`` output permute and, in backward, the
 ``dO`` permute and the scatter of dq / dk / dv into ONE packed ``[B, T, 3*H*Dh]`` gradient are
@@ -68,8 +68,8 @@ def native_attention_forward(qkv: torch.Tensor, n_head: int, causal: bool = True
                              scale: Optional[float] = None, return_lse: bool = False):
     """Forward-only attention on the package's own tcgen05 kernel (csrc/attn/attn_fwd_sm100.cu):
     q, k, v are read in place from the packed projection, the output is written in ``[B, T, H*Dh]``
-    layout, no layout copies at all.  head_dim 64, ``T % 128 == 0``.  No autograd (a backward
-    kernel does not exist yet): used for evaluation / inference when ``TDP_ATTN=native``."""
+    layout, no layout copies at all.  head_dim 64, ``T % 128 == 0``.  (``_NativeAttnFn`` adds the
+    backward kernel; both are selected with ``TDP_ATTN=native``.)"""
     C = native(required=True)
     B, T, D3 = qkv.shape
     D = D3 // 3
@@ -83,14 +83,45 @@ def native_attention_forward(qkv: torch.Tensor, n_head: int, causal: bool = True
     return (out, lse) if return_lse else out
 
 
-def _use_native_attention(qkv: torch.Tensor, n_head: int) -> bool:
+class _NativeAttnFn(torch.autograd.Function):
+    """Forward and backward on the package's tcgen05 attention kernels.  q, k, v are read in place
+    from the packed projection; dk and dv are written by TMA straight into their column windows of
+    the packed gradient; dq is accumulated in fp32 across key tiles and cast into its window."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_head: int, causal: bool, scale: float):
+        out, lse = native_attention_forward(qkv, n_head, causal, scale, return_lse=True)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (n_head, causal, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        C = native(required=True)
+        qkv, out, lse = ctx.saved_tensors
+        H, causal, scale = ctx.cfg
+        B, T, D3 = qkv.shape
+        dh = D3 // 3 // H
+        dout = dout.contiguous()
+        do4, o4 = dout.view(B, T, H, dh), out.view(B, T, H, dh)
+        delta = (do4.float() * o4.float()).sum(-1).permute(0, 2, 1).contiguous()      # [B, H, T]
+        qkv5 = qkv.view(B, T, 3, H, dh)
+        dqkv = torch.empty_like(qkv)
+        dqkv5 = dqkv.view(B, T, 3, H, dh)
+        dq_acc = torch.empty(B, T, H, dh, dtype=torch.float32, device=qkv.device)
+        C.attn_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], do4, lse, delta, dq_acc,
+                   dqkv5[:, :, 1], dqkv5[:, :, 2], bool(causal), float(scale))
+        dqkv5[:, :, 0].copy_(dq_acc)
+        return dqkv, None, None, None
+
+
+def _native_attention_enabled(qkv: torch.Tensor, n_head: int) -> bool:
     import os
     if os.environ.get("TDP_ATTN", "library") != "native":
         return False
     B, T, D3 = qkv.shape
     dh = D3 // 3 // n_head
-    return (not (torch.is_grad_enabled() and qkv.requires_grad)) and dh == 64 and T % 128 == 0 \
-        and qkv.dtype == torch.bfloat16 and hasattr(native(), "attn_fwd")
+    return dh == 64 and T % 128 == 0 and qkv.dtype == torch.bfloat16 and hasattr(native(), "attn_bwd")
 
 
 def packed_attention(qkv: torch.Tensor, n_head: int, causal: bool = True,
@@ -99,8 +130,12 @@ def packed_attention(qkv: torch.Tensor, n_head: int, causal: bool = True,
     B, T, D3 = qkv.shape
     D = D3 // 3
     dh = D // n_head
-    if native() is not None and qkv.is_cuda and qkv.is_contiguous() and _use_native_attention(qkv, n_head):
-        return native_attention_forward(qkv, n_head, causal, scale)
+    if native() is not None and qkv.is_cuda and qkv.is_contiguous() \
+            and _native_attention_enabled(qkv, n_head):
+        sc = float(scale if scale is not None else dh ** -0.5)
+        if torch.is_grad_enabled() and qkv.requires_grad:
+            return _NativeAttnFn.apply(qkv, n_head, causal, sc)
+        return native_attention_forward(qkv, n_head, causal, sc)
     if native() is not None and qkv.is_cuda and qkv.dtype in (torch.bfloat16, torch.float16) \
             and (dh * qkv.element_size()) % 16 == 0 and qkv.is_contiguous():
         return _PackedAttnFn.apply(qkv, n_head, causal, scale)
