@@ -319,6 +319,10 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
       p.epi_aux_tma = 1;
   }
 
+  // opt-in: two decoupled epilogue groups (see gemm_sm100.cuh); plain TMA-store GEMMs only
+  static const bool env_epi_split = [] { const char* v = getenv("TDP_GEMM_EPI"); return v && !strcmp(v, "split"); }();
+  p.epi_split = (env_epi_split && p.use_tma_store && p.comm_mode == COMM_NONE && g.split_k <= 1) ? 1 : 0;
+
   // split-K (weight-gradient shapes: few output tiles, very long K): partials are added with
   // vector atomics into an fp32 output that the caller zero-initialised (or accumulates into)
   p.split_k = 1;

@@ -62,6 +62,7 @@ struct GemmParams {
   int use_tma_store;
   int epi_in_tma;    // 1: residual, 2: dGELU input -- the [128 x 64] sub-tile arrives through TMA
   int epi_aux_tma;   // pre-activation copy (aux_out) leaves through smem + TMA store
+  int epi_split;     // two independent 4-warp epilogue groups, one per accumulator stage (opt-in)
   float alpha;
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, ld_res] or null
@@ -371,7 +372,7 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], kNumEpilogueWarps);
+      mbar_init(&tmem_empty_bar[i], p.epi_split ? kNumEpilogueWarps / 2 : kNumEpilogueWarps);
       mbar_init(&in_bar[i], 1);
     }
     fence_barrier_init();
@@ -482,6 +483,98 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
         acc_phase ^= 1;
       }
     }
+  } else if (warp_idx < 2 + kNumEpilogueWarps && p.epi_split) {
+    // ================================ epilogue, split in two groups ================================
+    // Group g (warps 2-5 / 6-9, one warp per TMEM lane quadrant) drains accumulator stage g, i.e.
+    // every second tile, on its own: own staging buffer, own named barrier, own TMA-store bulk
+    // groups.  The two groups never wait for each other, so the exposed latencies of one (TMEM
+    // load, input-tile TMA, store read-out) are filled by the other.  [opt-in: TDP_GEMM_EPI=split]
+    const int g = (warp_idx - 2) >> 2;
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    const bool issuer = (quad == 2) && (lane == 0);        // warps 2 and 6 open their groups
+    const int row_in_tile = quad * 32 + lane;
+    const int swz = row_in_tile & 7;
+    const bool in_tma = p.epi_in_tma != 0;
+    const bool aux_tma = p.epi_aux_tma != 0;
+    uint8_t* buf = smem_store + g * kStoreBytes;
+    uint8_t* brow = buf + row_in_tile * 128;
+    uint32_t in_phase = 0;
+    int t = 0;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); };
+    for (WorkIter it(p); it.next(p); ++t) {
+      if ((t & 1) != g) continue;
+      int m_blk, n_blk;
+      tile_to_mn(p, it.tile, m_blk, n_blk);
+      const int row = m_blk * kBlockM + row_in_tile;
+      const int n0 = n_blk * BLOCK_N;
+      const bool row_ok = row < p.M;
+      const int n_sub = (min(BLOCK_N, p.N - n0) + kStoreCols - 1) / kStoreCols;
+      mbar_wait(&tmem_full_bar[g], (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + g * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int sc = sub * kStoreCols;
+        if (issuer) {
+          tma_store_wait_read<0>();                          // my previous store has left the buffer
+          if (in_tma) {
+            mbar_expect_tx(&in_bar[g], kStoreBytes);
+            tma_load_2d(&tmap_in, &in_bar[g], buf, n0 + sc, m_blk * kBlockM);
+          }
+        }
+        group_sync();
+        if (in_tma) {
+          mbar_wait(&in_bar[g], in_phase);
+          in_phase ^= 1u;
+        }
+        uint32_t packed[2][16];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + sc + h * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + sc + h * 32;
+          f32x2 v[16];
+          epilogue_load_acc(p, r, v);
+          if (row_ok && col0 < p.N)
+            epilogue_math(p, v, row, col0, col0 + 32 <= p.N, in_tma ? brow : nullptr,
+                          aux_tma ? brow : nullptr, h, swz);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[h][i] = f32x2_to_bf16x2(v[i]);
+        }
+        if (sub == n_sub - 1) {
+          tc_fence_before();                                 // last TMEM read of this tile
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[g]);
+        }
+        if (aux_tma) {
+          // the buffer holds the pre-activation copy: send it, then reuse the buffer for C
+          fence_proxy_async_smem();
+          group_sync();
+          if (issuer) {
+            tma_store_2d(&tmap_aux, buf, n0 + sc, m_blk * kBlockM);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          group_sync();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(brow + (((h * 4 + j) ^ swz) * 16)) =
+                make_uint4(packed[h][4 * j], packed[h][4 * j + 1], packed[h][4 * j + 2],
+                           packed[h][4 * j + 3]);
+        fence_proxy_async_smem();
+        group_sync();
+        if (issuer) {
+          tma_store_2d(&store_maps.m[0], buf, n0 + sc, m_blk * kBlockM);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
   } else if (warp_idx < 2 + kNumEpilogueWarps) {
     // ================================ epilogue warps ================================
     // A warp may only touch TMEM lanes [32*(warp_idx%4), +32).
