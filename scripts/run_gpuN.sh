@@ -8,6 +8,8 @@ TR 150 29511 scripts/symm_check.py > gpurun_out/symm_check_w$N.log 2>&1
 grep -vE "$F" gpurun_out/symm_check_w$N.log | grep -E "multicast|ALL_OK|FAIL|Error|gemm_rs|ag_gemm|'MiB': 256" | cut -c1-300 | tail -8
 TR 150 29512 scripts/tp_check.py > gpurun_out/tp_check_w$N.log 2>&1
 grep -vE "$F" gpurun_out/tp_check_w$N.log | grep -v "spin wait" | tail -5 | cut -c1-300
+TR 150 29518 scripts/ddp_debug.py > gpurun_out/ddp_debug_w$N.log 2>&1
+grep -vE "$F" gpurun_out/ddp_debug_w$N.log | grep -E "^A raw|mismatching|DONE|Error" | tail -10 | cut -c1-300
 TR 150 29513 scripts/engines_check.py > gpurun_out/engines_check_w$N.log 2>&1
 grep -vE "$F" gpurun_out/engines_check_w$N.log | grep -v "spin wait" | tail -8 | cut -c1-300
 for impl in reference ours; do
