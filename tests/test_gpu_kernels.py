@@ -194,6 +194,24 @@ def test_gpt2_native_step_matches_torch_reference():
     assert all(torch.isfinite(p.grad).all() for p in model.parameters())
 
 
+def test_graft_smoke():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.smoke()
+
+
+@pytest.mark.multigpu
+def test_multi_gpu_collectives_and_fused_tp():
+    """Runs the 2-GPU numerics scripts (symmetric collectives, fused GEMM+collective, TP block)."""
+    n = 2
+    for script, port in (("scripts/symm_check.py", 29621), ("scripts/tp_check.py", 29622)):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                            f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
+                            str(port), os.path.join(ROOT, script)], cwd=ROOT, capture_output=True,
+                           text=True, timeout=240)
+        assert r.returncode == 0 and "ALL_OK True" in r.stdout, (script, r.stdout[-3000:], r.stderr[-3000:])
+
+
 def test_ddp_direct_weight_gradients_match_autograd():
     """NaiveDDP bucket views + ops.linear.wgrad: weight gradients written straight into the
     bucket (overwrite on the first micro-step, accumulate on the second) equal the gradients
@@ -220,21 +238,3 @@ def test_ddp_direct_weight_gradients_match_autograd():
             ref = p.grad.float()
             err = (q.grad.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
             assert err < 3e-2, (step, n, err)
-
-
-def test_graft_smoke():
-    sys.path.insert(0, ROOT)
-    import __graft_entry__ as g
-    g.smoke()
-
-
-@pytest.mark.multigpu
-def test_multi_gpu_collectives_and_fused_tp():
-    """Runs the 2-GPU numerics scripts (symmetric collectives, fused GEMM+collective, TP block)."""
-    n = 2
-    for script, port in (("scripts/symm_check.py", 29621), ("scripts/tp_check.py", 29622)):
-        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
-                            f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port",
-                            str(port), os.path.join(ROOT, script)], cwd=ROOT, capture_output=True,
-                           text=True, timeout=240)
-        assert r.returncode == 0 and "ALL_OK True" in r.stdout, (script, r.stdout[-3000:], r.stderr[-3000:])
