@@ -319,3 +319,23 @@ def test_async_checkpoint_writer_roundtrip(tmp_path):
     w.save(str(tmp_path / "no" / "\0bad"), {"x": torch.ones(1)})        # unwritable path
     with pytest.raises(RuntimeError):
         w.wait()
+
+
+def test_int8_weight_only_linear_replacement():
+    import torch.nn as nn
+    from torchdistpackage_b200.tools import (Int8WeightOnlyLinear, replace_linear_by_int8,
+                                             replace_linear_by_bnb)
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(64, 128), nn.GELU(), nn.Sequential(nn.Linear(128, 32, bias=False)))
+    x = torch.randn(5, 64)
+    ref = model(x)
+    n_before = sum(p.numel() * p.element_size() for p in model.parameters())
+    replace_linear_by_int8(model)
+    assert isinstance(model[0], Int8WeightOnlyLinear) and isinstance(model[2][0], Int8WeightOnlyLinear)
+    out = model(x)
+    assert (out - ref).abs().max() / ref.abs().max() < 2e-2          # 8-bit per-channel weights
+    n_after = sum(t.numel() * t.element_size() for t in list(model.parameters()) + list(model.buffers()))
+    assert n_after < 0.4 * n_before                                   # fp32 -> int8 (+ scales, bias)
+    assert model[0].weight_q.dtype == torch.int8 and "0.weight_q" in model.state_dict()
+    with pytest.raises(ImportError):
+        replace_linear_by_bnb(nn.Sequential(nn.Linear(4, 4)))         # optional dependency absent

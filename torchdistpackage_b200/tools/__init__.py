@@ -4,3 +4,6 @@ from .debug_nan import (check_tensors, check_model_params, fwd_hook_wrapper, bwd
                         register_nan_hooks)
 from .watchdog import StepWatchdog, HANG_EXIT_CODE
 from .metrics import MetricsLogger
+from .int8_linear import Int8WeightOnlyLinear, replace_linear_by_int8
+from .bnb_fc import replace_linear_by_bnb
+from .bminf_int8 import replace_linear_by_bminf

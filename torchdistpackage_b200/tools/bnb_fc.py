@@ -1,15 +1,16 @@
-"""bitsandbytes int8 linear replacement (reference: tools/bnb_fc.py:1-22).  Optional: importing
-this module fails cleanly when bitsandbytes is not installed (it is not part of the B200 image;
-note that sm_100 has INT8 tensor cores but the bf16 / fp8 tcgen05 paths are what this package
-targets)."""
-import torch
+"""bitsandbytes int8 linear replacement (reference: tools/bnb_fc.py:1-22).  Optional: the library
+is imported on first use (it is not installed in the B200 image; ``tools.int8_linear`` is the
+self-contained alternative)."""
 import torch.nn as nn
-import bitsandbytes as bnb  # noqa: F401  (ImportError is handled by the package root)
 
 from .module_replace import replace_all_module
 
 
 def _to_bnb(fc: nn.Linear) -> nn.Module:
+    try:
+        import bitsandbytes as bnb
+    except ImportError as e:       # not in the B200 image: tools.int8_linear is the in-tree option
+        raise ImportError("bitsandbytes is not installed; use tools.replace_linear_by_int8") from e
     has_bias = fc.bias is not None
     new = bnb.nn.Linear8bitLt(fc.in_features, fc.out_features, bias=has_bias,
                               has_fp16_weights=False, threshold=6.0)
