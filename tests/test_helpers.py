@@ -339,3 +339,56 @@ def test_int8_weight_only_linear_replacement():
     assert model[0].weight_q.dtype == torch.int8 and "0.weight_q" in model.state_dict()
     with pytest.raises(ImportError):
         replace_linear_by_bnb(nn.Sequential(nn.Linear(4, 4)))         # optional dependency absent
+
+
+def test_grouped_mlp_coordinate_mapping(monkeypatch):
+    """ops.grouped drives one grouped GEMM per product; here the kernel is emulated with torch
+    following the launcher's contract (group g of C rows reads A / B at coordinate offsets
+    g * {a_m, a_k, b_n, b_k}) and the result is compared with a per-expert loop, forward and all
+    gradients.  Checks the operand views / offsets the Python side hands to the kernel."""
+    import torch.nn.functional as F
+    from torchdistpackage_b200.ops import grouped as Gm
+    from torchdistpackage_b200.ops import linear as L
+
+    def emu(a, b, c, trans_a, trans_b, N, K, grp_rows, a_m=0, a_k=0, b_n=0, b_k=0, bias=None,
+            aux_in=None, aux_out=None, act=0):
+        G = c.shape[0] // grp_rows
+        for g in range(G):
+            r0 = g * grp_rows
+            m_lo, k_lo = r0 + g * a_m, g * a_k
+            A = a[k_lo:k_lo + K, m_lo:m_lo + grp_rows].t() if trans_a else a[m_lo:m_lo + grp_rows, k_lo:k_lo + K]
+            n_lo, kb_lo = g * b_n, g * b_k
+            B = b[n_lo:n_lo + N, kb_lo:kb_lo + K].t() if trans_b else b[kb_lo:kb_lo + K, n_lo:n_lo + N]
+            assert A.shape == (grp_rows, K) and B.shape == (K, N), (A.shape, B.shape)
+            y = A.double() @ B.double()
+            if bias is not None:
+                y = y + bias.view(G, N)[g].double()
+            if aux_out is not None:
+                aux_out[r0:r0 + grp_rows] = y.to(aux_out.dtype)
+            if act == L.ACT_GELU_TANH:
+                y = F.gelu(y, approximate="tanh")
+            if act == L.ACT_DGELU_TANH:
+                with torch.enable_grad():
+                    zz = aux_in[r0:r0 + grp_rows].double().requires_grad_(True)
+                    d, = torch.autograd.grad(F.gelu(zz, approximate="tanh").sum(), zz)
+                y = y * d
+            c[r0:r0 + grp_rows] = y.to(c.dtype)
+
+    monkeypatch.setattr(Gm, "_cgemm", lambda: emu)
+    torch.manual_seed(0)
+    E, R, dim, hidden = 3, 4, 6, 10
+    dt = torch.float64
+    x = torch.randn(E * R, dim, dtype=dt, requires_grad=True)
+    w1 = (torch.randn(E, dim, hidden, dtype=dt) * 0.3).requires_grad_(True)
+    b1 = torch.randn(E, hidden, dtype=dt, requires_grad=True)
+    w2 = (torch.randn(E, hidden, dim, dtype=dt) * 0.3).requires_grad_(True)
+    b2 = torch.randn(E, dim, dtype=dt, requires_grad=True)
+    y = Gm.grouped_mlp(x, w1, b1, w2, b2)
+    gy = torch.randn_like(y)
+    got = torch.autograd.grad(y, (x, w1, b1, w2, b2), gy)
+    ref = torch.cat([F.gelu(x[e * R:(e + 1) * R] @ w1[e] + b1[e], approximate="tanh") @ w2[e] + b2[e]
+                     for e in range(E)])
+    want = torch.autograd.grad(ref, (x, w1, b1, w2, b2), gy)
+    assert torch.allclose(y, ref, atol=1e-10)
+    for name, g_, w_ in zip(("dx", "dw1", "db1", "dw2", "db2"), got, want):
+        assert torch.allclose(g_, w_, atol=1e-8), name

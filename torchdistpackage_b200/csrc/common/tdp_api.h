@@ -44,6 +44,11 @@ struct GemmLaunch {
   uint32_t flag_target;
   void* peer_out[kApiMaxPeers];
   uint32_t* peer_tile_counter[kApiMaxPeers];
+  // grouped GEMM (MoE experts stacked along M): rows_per_group % 128 == 0 rows of C form a group;
+  // group g reads its operands at coordinate offsets g * {a_m, a_k, b_n, b_k} (elements) and adds
+  // bias + g * bias_stride.  M, N, K describe ONE group's product except M = all groups' rows.
+  int grp_rows;          // 0 = plain GEMM
+  int grp_a_m, grp_a_k, grp_b_n, grp_b_k, grp_bias;
   // AG mode, push folded into the GEMM: a_local (contiguous) is copied by an extra warp of every
   // CTA to push_dst[r] (+ my own slot) / push_mc, then push_flag[r] = flag_target is published
   int push;

@@ -236,13 +236,31 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     p.group_m = gm;
   }
 
+  // grouped GEMM: operand extents cover all groups along whichever coordinate is shifted per group
+  uint64_t a_m_ext = g.M, a_k_ext = g.K, b_n_ext = g.N, b_k_ext = g.K;
+  if (g.grp_rows > 0) {
+    if (g.grp_rows % kBlockM || g.M % g.grp_rows || g.K % kBlockK || g.comm_mode != 0 ||
+        g.split_k > 1 || (g.grp_b_n != 0 && g.N % block_n)) {
+      snprintf(msg, sizeof(msg), "gemm(grouped): rows/group %% 128, K %% 64 (and N %% tile for "
+               "N-stacked B) must be 0; no collective / split-K modes");
+      return -1;
+    }
+    const uint64_t G = g.M / g.grp_rows;
+    p.grp_mblocks = g.grp_rows / kBlockM;
+    p.grp_a_m = g.grp_a_m; p.grp_a_k = g.grp_a_k; p.grp_b_n = g.grp_b_n; p.grp_b_k = g.grp_b_k;
+    p.grp_bias = g.grp_bias;
+    if (g.grp_a_m != 0) a_m_ext = g.grp_rows;           // A's M extent is one group's rows
+    if (g.grp_a_k != 0) a_k_ext = g.K * G;
+    if (g.grp_b_n != 0) b_n_ext = g.N * G;
+    if (g.grp_b_k != 0) b_k_ext = g.K * G;
+  }
   CUtensorMap ta, tb;
   bool ok;
-  if (!g.trans_a) ok = make_tmap_2d(&ta, g.a, g.K, g.M, g.lda, kBlockK, kBlockM);
-  else            ok = make_tmap_2d(&ta, g.a, g.M, g.K, g.lda, 64, kBlockK);
+  if (!g.trans_a) ok = make_tmap_2d(&ta, g.a, a_k_ext, a_m_ext, g.lda, kBlockK, kBlockM);
+  else            ok = make_tmap_2d(&ta, g.a, a_m_ext, a_k_ext, g.lda, 64, kBlockK);
   if (!ok) { snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(A) failed"); return -2; }
-  if (g.trans_b)  ok = make_tmap_2d(&tb, g.b, g.K, g.N, g.ldb, kBlockK, block_n);
-  else            ok = make_tmap_2d(&tb, g.b, g.N, g.K, g.ldb, 64, kBlockK);
+  if (g.trans_b)  ok = make_tmap_2d(&tb, g.b, b_k_ext, b_n_ext, g.ldb, kBlockK, block_n);
+  else            ok = make_tmap_2d(&tb, g.b, b_n_ext, b_k_ext, g.ldb, 64, kBlockK);
   if (!ok) { snprintf(msg, sizeof(msg), "gemm: cuTensorMapEncodeTiled(B) failed"); return -2; }
 
   // local (un-gathered) A shard for the all-gather variant: zero-copy, never waits
@@ -355,7 +373,7 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
   static const int env_2cta = [] { const char* v = getenv("TDP_GEMM_2CTA"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
   bool auto_2cta = g.K >= 2048 && g.act == ACT_NONE && g.aux_out == nullptr;
   if (env_2cta >= 0) auto_2cta = env_2cta == 1;
-  if ((g.cta_group == 2 || (g.cta_group == 0 && auto_2cta)) && p.comm_mode == COMM_NONE &&
+  if (g.grp_rows == 0 && (g.cta_group == 2 || (g.cta_group == 0 && auto_2cta)) && p.comm_mode == COMM_NONE &&
       p.split_k == 1 && p.use_tma_store && g.N > 128 && g.M > 128) {
     GemmParams q = p;
     q.num_m_blocks = (g.M + 2 * kBlockM - 1) / (2 * kBlockM);

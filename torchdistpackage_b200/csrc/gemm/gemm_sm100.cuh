@@ -63,6 +63,11 @@ struct GemmParams {
   int epi_in_tma;    // 1: residual, 2: dGELU input -- the [128 x 64] sub-tile arrives through TMA
   int epi_aux_tma;   // pre-activation copy (aux_out) leaves through smem + TMA store
   int epi_split;     // two independent 4-warp epilogue groups, one per accumulator stage (opt-in)
+  // grouped GEMM (MoE experts): output row-block m belongs to group m / grp_mblocks; the TMA
+  // coordinates of the operands are shifted by group * these element offsets (0 = not grouped)
+  int grp_mblocks;
+  int grp_a_m, grp_a_k, grp_b_n, grp_b_k;
+  int grp_bias;      // bias element offset per group
   float alpha;
   const __nv_bfloat16* bias;      // [N] or null
   const __nv_bfloat16* residual;  // [M, ld_res] or null
@@ -186,10 +191,13 @@ TDP_DEVICE void epilogue_math(const GemmParams& p, f32x2 (&v)[16], int row, int 
                               const uint8_t* in_row = nullptr, uint8_t* z_row = nullptr, int h = 0,
                               int swz = 0) {
   if (p.bias != nullptr) {
+    // grouped GEMM: one bias vector per group (expert) of output rows
+    const __nv_bfloat16* bias =
+        p.bias + (p.grp_mblocks > 0 ? (row / (p.grp_mblocks * kBlockM)) * p.grp_bias : 0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (full || col0 + 8 * j + 8 <= p.N) {
-        const uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + 8 * j);
+        const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + 8 * j);
         v[4 * j] = add2(v[4 * j], bf16x2_to_f32x2(b.x));
         v[4 * j + 1] = add2(v[4 * j + 1], bf16x2_to_f32x2(b.y));
         v[4 * j + 2] = add2(v[4 * j + 2], bf16x2_to_f32x2(b.z));
@@ -412,6 +420,10 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         const int n0 = n_blk * BLOCK_N;
+        // grouped mode: shift the operand windows to this tile's group (expert)
+        const int grp = p.grp_mblocks > 0 ? m_blk / p.grp_mblocks : 0;
+        const int a_m0 = m0 + grp * p.grp_a_m, a_koff = grp * p.grp_a_k;
+        const int b_n0 = n0 + grp * p.grp_b_n, b_koff = grp * p.grp_b_k;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
@@ -419,18 +431,20 @@ gemm_bf16_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a,
           uint8_t* sb = smem_b + stage * S::kStageBytesB;
           const int k0 = kb * kBlockK;
           if (!p.a_mn_major) {
-            tma_load_2d(amap, &full_bar[stage], sa, k0, m0);
+            tma_load_2d(amap, &full_bar[stage], sa, k0 + a_koff, a_m0);
           } else {
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_2d(amap, &full_bar[stage], sa + j * (64 * kBlockK * 2), m0 + 64 * j, k0);
+              tma_load_2d(amap, &full_bar[stage], sa + j * (64 * kBlockK * 2), a_m0 + 64 * j,
+                          k0 + a_koff);
           }
           if (!p.b_mn_major) {
-            tma_load_2d(&tmap_b, &full_bar[stage], sb, k0, n0);
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, k0 + b_koff, b_n0);
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (64 * kBlockK * 2), n0 + 64 * j, k0);
+              tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (64 * kBlockK * 2), b_n0 + 64 * j,
+                          k0 + b_koff);
           }
           if (++stage == kStages) {
             stage = 0;

@@ -29,6 +29,9 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
+from ..ops import grouped
 from ..ops import linear as L
 from ..ops._loader import native
 from ..ops.symm import get_symm_group
@@ -205,6 +208,9 @@ class _CombineFn(torch.autograd.Function):
         return d_slots.clone(), dw.to(weight.dtype), None, None
 
 
+_MOE_GROUPED = os.environ.get("TDP_MOE_GROUPED", "0") == "1"
+
+
 class Experts(nn.Module):
     """``num_local`` independent MLPs with stacked weights ``[E_local, in, out]``."""
 
@@ -220,6 +226,9 @@ class Experts(nn.Module):
 
     def forward(self, slots: torch.Tensor) -> torch.Tensor:
         """slots [E_local * rows_per_expert, dim]"""
+        if _MOE_GROUPED and grouped.grouped_supported(slots, self.w1, self.w2):
+            # all local experts in one persistent launch per GEMM (opt-in, see ops/grouped.py)
+            return grouped.grouped_mlp(slots, self.w1, self.b1, self.w2, self.b2, act="gelu_tanh")
         rows = slots.shape[0] // self.num_local
         outs = []
         for e in range(self.num_local):
