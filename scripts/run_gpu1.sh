@@ -7,6 +7,7 @@ T 200 python scripts/gemm_check.py > gpurun_out/gemm_check.log 2>&1; grep -E "AL
 TDP_GEMM_EPI=split TDP_GEMM_2CTA=0 T 200 python scripts/gemm_check.py > gpurun_out/gemm_check_epi_split.log 2>&1; grep -E "ALL_OK|'ok': False|Error" gpurun_out/gemm_check_epi_split.log | head -5
 T 150 python scripts/gemm2cta_check.py > gpurun_out/gemm2cta_check.log 2>&1; grep -E "ALL_OK|'ok': False|Error" gpurun_out/gemm2cta_check.log | tail -3
 T 150 python scripts/fused_check.py > gpurun_out/fused_check.log 2>&1; grep -E "all_ok|FAIL|Error" gpurun_out/fused_check.log | head -3
+T 150 python scripts/grouped_check.py > gpurun_out/grouped_check.log 2>&1; grep -E "ALL_OK|'ok': False|error" gpurun_out/grouped_check.log | tail -4 | cut -c1-300
 T 150 python scripts/attn_check.py > gpurun_out/attn_check.log 2>&1; grep -E "ALL_OK|'ok': False|ERROR|native_ms" gpurun_out/attn_check.log | tail -6
 T 250 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 T 200 python scripts/trace_step.py ours 2>&1 | grep -v Warning | sed -n 2,3p
