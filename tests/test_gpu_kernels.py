@@ -35,39 +35,6 @@ def test_gemm_operand_majors(ta, tb, block_n):
     assert rel(c, ref) < 1e-2
 
 
-@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
-@pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_2cta_pairs(ta, tb, block_n):
-    """cta_group::2 kernel (256 x {128|256} tile per CTA pair): operand majors, ragged edges and a
-    fused epilogue against the fp32 product."""
-    C = _C()
-    torch.manual_seed(2)
-    M, N, K = 1000, 760, 520
-    a = torch.randn((K, M) if ta else (M, K), device="cuda", dtype=torch.bfloat16)
-    b = torch.randn((N, K) if tb else (K, N), device="cuda", dtype=torch.bfloat16)
-    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
-    c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    C.gemm(a, b, c, ta, tb, bias=bias, block_n=block_n, cta_group=2)
-    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float()) + bias.float()
-    assert rel(c, ref) < 1e-2
-
-
-def test_gemm_auto_selection_long_k_and_weight_gradient_shapes():
-    """ops.linear.gemm picks the CTA-pair kernels for long-K products and 256x128 pair tiles for
-    weight-gradient shapes; results must not depend on the kernel that was selected."""
-    from torchdistpackage_b200.ops import linear as L
-    torch.manual_seed(3)
-    x = torch.randn(4096, 768, device="cuda", dtype=torch.bfloat16)
-    dy = torch.randn(4096, 3072, device="cuda", dtype=torch.bfloat16)
-    dw = L.gemm(x, dy, trans_a=True)                       # [768, 3072], K = 4096 tokens
-    assert rel(dw, x.float().t() @ dy.float()) < 1e-2
-    w = torch.randn(3072, 768, device="cuda", dtype=torch.bfloat16) * 0.05
-    y = L.gemm(dy, w)                                      # K = 3072 >= 2048: CTA pairs
-    assert rel(y, dy.float() @ w.float()) < 1e-2
-    small = L.gemm(x[:, :768], x[:, :768], trans_a=True)   # 768 x 768, K = 4096: stream-K
-    assert rel(small, x.float().t() @ x.float()) < 1e-2
-
-
 def test_gemm_fused_epilogues():
     C = _C()
     torch.manual_seed(1)
@@ -271,3 +238,36 @@ def test_ddp_direct_weight_gradients_match_autograd():
             ref = p.grad.float()
             err = (q.grad.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
             assert err < 3e-2, (step, n, err)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_2cta_pairs(ta, tb, block_n):
+    """cta_group::2 kernel (256 x {128|256} tile per CTA pair): operand majors, ragged edges and a
+    fused epilogue against the fp32 product."""
+    C = _C()
+    torch.manual_seed(2)
+    M, N, K = 1000, 760, 520
+    a = torch.randn((K, M) if ta else (M, K), device="cuda", dtype=torch.bfloat16)
+    b = torch.randn((N, K) if tb else (K, N), device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    C.gemm(a, b, c, ta, tb, bias=bias, block_n=block_n, cta_group=2)
+    ref = (a.float().t() if ta else a.float()) @ (b.float().t() if tb else b.float()) + bias.float()
+    assert rel(c, ref) < 1e-2
+
+
+def test_gemm_auto_selection_long_k_and_weight_gradient_shapes():
+    """ops.linear.gemm picks the CTA-pair kernels for long-K products and 256x128 pair tiles for
+    weight-gradient shapes; results must not depend on the kernel that was selected."""
+    from torchdistpackage_b200.ops import linear as L
+    torch.manual_seed(3)
+    x = torch.randn(4096, 768, device="cuda", dtype=torch.bfloat16)
+    dy = torch.randn(4096, 3072, device="cuda", dtype=torch.bfloat16)
+    dw = L.gemm(x, dy, trans_a=True)                       # [768, 3072], K = 4096 tokens
+    assert rel(dw, x.float().t() @ dy.float()) < 1e-2
+    w = torch.randn(3072, 768, device="cuda", dtype=torch.bfloat16) * 0.05
+    y = L.gemm(dy, w)                                      # K = 3072 >= 2048: CTA pairs
+    assert rel(y, dy.float() @ w.float()) < 1e-2
+    small = L.gemm(x[:, :768], x[:, :768], trans_a=True)   # 768 x 768, K = 4096: stream-K
+    assert rel(small, x.float().t() @ x.float()) < 1e-2
