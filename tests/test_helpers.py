@@ -236,9 +236,12 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
             self.w2 = nn.Parameter(torch.randn(32, 16) * 0.1)
             self.b2 = nn.Parameter(torch.zeros(16))
             self.w3 = nn.Parameter(torch.randn(16, 8) * 0.1)
+            self.w_tied = nn.Parameter(torch.randn(16, 16) * 0.1)
 
         def forward(self, x):
             h = L.mlp(x, self.w1, self.b1, self.w2, self.b2, layout="kn", act="gelu_tanh", residual=x)
+            h = L.linear(h, self.w_tied, None, layout="kn")          # the same weight used twice:
+            h = L.linear(h, self.w_tied, None, layout="kn", residual=h)   # final only after both
             return L.linear(h, self.w3, None, layout="kn").float().pow(2).mean()
 
     torch.manual_seed(0)
@@ -250,15 +253,22 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
         if p.dim() == 2:
             p._tdp_main_grad = red.param_bucket[name].views[name]
             p._tdp_grad_fresh = True
-            p._tdp_on_grad_ready = red._make_direct_ready(name, p)
+    ready_calls = []
+    orig_ready = red._on_grad_ready
+    monkeypatch.setattr(red, "_on_grad_ready", lambda n, p: (ready_calls.append(n), orig_ready(n, p))[1])
     xs = [torch.randn(8, 16).to(torch.bfloat16) for _ in range(2)]
     for _ in range(2):
         base.zero_grad(set_to_none=True)
         ddp.zero_grad()                           # in-place on bucket views
+        ready_calls.clear()
         for x in xs:
             base(x).backward()
             ddp(x).backward()
         ddp.reduce_gradients()
+        # every parameter is reported exactly once per micro-step (by autograd's post-accumulate
+        # hook, which also runs for the undefined gradients the direct path returns) -- the tied
+        # weight only after both of its uses have written their share
+        assert sorted(ready_calls) == sorted(list(red.params) * len(xs)), " ".join(ready_calls)
         for (n, p), (_, q) in zip(base.named_parameters(), wrapped.named_parameters()):
             assert q.grad.data_ptr() == red.param_bucket[n].views[n].data_ptr(), n
             assert torch.allclose(q.grad.float(), p.grad.float(), rtol=2e-2, atol=1e-3), n

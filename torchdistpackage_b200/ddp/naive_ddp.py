@@ -207,7 +207,6 @@ class _GradReducer:
                         # lets ops.linear.wgrad write the weight gradient straight into the bucket
                         p._tdp_main_grad = view
                         p._tdp_grad_fresh = True
-                        p._tdp_on_grad_ready = self._make_direct_ready(name, p)
             self.buckets.append(bucket)
 
     # ------------------------------------------------------------------ hooks
@@ -222,17 +221,12 @@ class _GradReducer:
             self._on_grad_ready(name, p)
         return hook
 
-    def _make_direct_ready(self, name: str, p: torch.nn.Parameter):
-        def ready():
-            self._on_grad_ready(name, p)
-        return ready
-
     def remove_hooks(self) -> None:
         for h in self._hooks:
             h.remove()
         self._hooks = []
         for p in self.params.values():
-            for attr in ("_tdp_main_grad", "_tdp_grad_fresh", "_tdp_on_grad_ready"):
+            for attr in ("_tdp_main_grad", "_tdp_grad_fresh"):
                 if hasattr(p, attr):
                     delattr(p, attr)
 

@@ -118,9 +118,11 @@ def wgrad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
 
     If ``w.grad`` is a view of a gradient bucket that a reducer (NaiveDDP) registered on the
     parameter (``w._tdp_main_grad``), the GEMM epilogue writes the bucket directly -- overwriting on
-    the first micro-step after a reduction, accumulating afterwards -- the reducer is told the
-    gradient is final, and ``None`` is returned to autograd: no temporary, no ``grad += dw``
-    kernel per parameter.  Otherwise returns the gradient tensor for autograd to accumulate."""
+    the first micro-step after a reduction, accumulating afterwards -- and ``None`` is returned to
+    autograd: no temporary, no ``grad += dw`` kernel per parameter.  Readiness is still reported by
+    the reducer's post-accumulate-grad hook: autograd runs it once per parameter and backward pass
+    even for an undefined gradient, after *all* uses of the parameter (tied weights) have run their
+    backward.  Otherwise returns the gradient tensor for autograd to accumulate."""
     buf = getattr(w, "_tdp_main_grad", None)
     if buf is None or w.grad is None or w.grad.data_ptr() != buf.data_ptr() \
             or getattr(w, "_tdp_no_fused_wgrad", False) or not _FUSED_WGRAD:
@@ -130,7 +132,6 @@ def wgrad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
         w._tdp_grad_fresh = False
     else:
         gemm(a, b, trans_a=True, out=buf, accumulate=True)
-    w._tdp_on_grad_ready()
     return None
 
 
