@@ -488,3 +488,80 @@ def _fd_share_worker(rank, world):
 def test_symm_fd_passing():
     """native symmetric-memory backend: POSIX fds travel between ranks with SCM_RIGHTS"""
     run_distributed(_fd_share_worker, 3)
+
+
+# ------------------------------------------------------------------ DDP + direct weight gradients
+def _w_ddp_direct_wgrad(rank, world):
+    """Two ranks, ops.linear layers (kernel emulated with torch), weight gradients written straight
+    into the NaiveDDP bucket views: buckets must be reduced only when every gradient is final."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.ops import linear as L
+
+    def fake_gemm(a, b, *, trans_a=False, trans_b=False, out=None, out_dtype=None, bias=None,
+                  residual=None, aux_in=None, aux_out=None, act=0, accumulate=False, alpha=1.0, **kw):
+        y = ((a.t() if trans_a else a).double() @ (b.t() if trans_b else b).double()) * alpha
+        if bias is not None:
+            y = y + bias.double()
+        if aux_out is not None:
+            aux_out.copy_(y.to(aux_out.dtype))
+        if act == L.ACT_GELU_TANH:
+            y = F.gelu(y, approximate="tanh")
+        if act == L.ACT_DGELU_TANH:
+            with torch.enable_grad():
+                z = aux_in.double().requires_grad_(True)
+                g, = torch.autograd.grad(F.gelu(z, approximate="tanh").sum(), z)
+            y = y * g
+        if residual is not None:
+            y = y + residual.double()
+        if out is None:
+            return y.to(out_dtype or a.dtype)
+        out.add_(y.to(out.dtype)) if accumulate else out.copy_(y.to(out.dtype))
+        return out
+
+    L.gemm = fake_gemm
+    L._native_ok = lambda *ts: True
+    L.colsum = lambda x, out_dtype=None: x.sum(0).to(out_dtype or x.dtype)
+    L._FUSED_WGRAD = True
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w1 = nn.Parameter(torch.randn(8, 16) * 0.2)
+            self.b1 = nn.Parameter(torch.zeros(16))
+            self.w2 = nn.Parameter(torch.randn(16, 8) * 0.2)
+            self.b2 = nn.Parameter(torch.zeros(8))
+            self.w_tied = nn.Parameter(torch.randn(8, 8) * 0.2)
+
+        def forward(self, x):
+            h = L.mlp(x, self.w1, self.b1, self.w2, self.b2, layout="kn", act="gelu_tanh", residual=x)
+            h = L.linear(h, self.w_tied, None, layout="kn")
+            return L.linear(h, self.w_tied, None, layout="kn", residual=h).pow(2).mean()
+
+    tdp.fix_rand(0)
+    model = Net().double()
+    ref = copy.deepcopy(model)
+    ddp = tdp.NaiveDDP(model, gradient_as_bucket_view=True, bucket_cap_mb=1e-4, num_grad_acc_iter=2)
+    red = ddp.reducer
+    for name, p in red.params.items():             # what the reducer does itself on CUDA
+        if p.dim() == 2:
+            p._tdp_main_grad = red.param_bucket[name].views[name]
+            p._tdp_grad_fresh = True
+    for step in range(2):
+        ddp.zero_grad()
+        ref.zero_grad(set_to_none=True)
+        for mb in range(2):
+            torch.manual_seed(1000 * step + 10 * mb + rank)
+            ddp(torch.randn(4, 8, dtype=torch.double)).backward()
+        ddp.reduce_gradients()
+        for mb in range(2):
+            for r in range(world):
+                torch.manual_seed(1000 * step + 10 * mb + r)
+                (ref(torch.randn(4, 8, dtype=torch.double)) / world).backward()
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-10), (step, n)
+
+
+def test_naive_ddp_direct_weight_gradients_two_ranks():
+    run_distributed(_w_ddp_direct_wgrad, 2)
