@@ -295,3 +295,59 @@ def backward_roles(n_iter, q_stages=2):
 def test_backward_protocol(n_iter):
     for seed in range(40):
         run(backward_roles(n_iter), seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM with the split epilogue (gemm_sm100.cuh, TDP_GEMM_EPI=split): two epilogue groups, one per
+# TMEM accumulator stage; the MMA warp alternates stages per tile
+# ------------------------------------------------------------------------------------------------
+def split_epilogue_roles(n_tiles):
+    tmem_full = [MBar(1), MBar(1)]
+    tmem_empty = [MBar(4), MBar(4)]          # four warps of the owning group arrive
+    ACC = [Resource("acc0"), Resource("acc1")]
+    pending = []
+    done = {"mma": False}
+
+    def mma_engine():
+        while True:
+            if pending:
+                for b in pending.pop(0):
+                    b.arrive()
+                yield True
+            else:
+                yield False
+                if done["mma"] and not pending:
+                    return
+
+    def mma():
+        acc, acc_phase = 0, 0
+        for t in range(n_tiles):
+            yield from wait(lambda: tmem_empty[acc].passed_fresh(acc_phase ^ 1))
+            ACC[acc].write(t)
+            pending.append([tmem_full[acc]])
+            yield True
+            acc += 1
+            if acc == 2:
+                acc, acc_phase = 0, acc_phase ^ 1
+        done["mma"] = True
+
+    def group(g):
+        for t in range(n_tiles):
+            if (t & 1) != g:
+                continue
+            yield from wait(lambda: tmem_full[g].passed((t >> 1) & 1))
+            ACC[g].begin_read(t)
+            yield True                                   # four sub-tiles of TMEM reads
+            yield True
+            ACC[g].end_read()
+            for _ in range(4):
+                tmem_empty[g].arrive()
+            yield True                                   # stores drain after the stage is freed
+
+    return [mma(), mma_engine(), group(0), group(1)]
+
+
+@pytest.mark.parametrize("n_tiles", [1, 2, 3, 7, 10, 11])
+def test_gemm_split_epilogue_protocol(n_tiles):
+    for seed in range(40):
+        run(split_epilogue_roles(n_tiles), seed)
