@@ -434,13 +434,12 @@ class NaiveDDP(torch.nn.Module):
     def set_num_grad_acc_iter(self, n: int) -> None:
         self.reducer.num_grad_acc_iter = max(int(n), 1)
 
-    def __del__(self):
-        # detach the gradient hooks and the direct-write attributes from the parameters: a model
-        # that outlives its wrapper must not keep reducing into this wrapper's buckets
-        try:
-            self.reducer.remove_hooks()
-        except Exception:
-            pass
+    def remove_hooks(self) -> None:
+        """Detach the gradient hooks (and the direct weight-gradient attributes) from the
+        parameters.  Not done automatically when the wrapper is garbage collected: the hooks keep
+        the reducer alive, so ``NaiveDDP(model)`` keeps synchronising even if the caller drops the
+        wrapper object and trains through ``model`` (as with the reference)."""
+        self.reducer.remove_hooks()
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # keep bucket views alive by default
         for p in self.module.parameters():
