@@ -324,6 +324,10 @@ class BucketAdamW:
         self.step_count = int(sd["step"])
         for g, sg in zip(self.param_groups, sd["param_groups"]):
             g.update(sg)
+        if self._hyper is not None:            # the device-resident {step, lr} the kernel reads
+            self._hyper[0].fill_(float(self.step_count))
+            self._hyper[1].fill_(float(self.param_groups[0]["lr"]))
+            self._hyper_lr = float(self.param_groups[0]["lr"])
         for s, ss in zip(self.state, sd["buckets"]):
             s["exp_avg"].copy_(ss["exp_avg"])
             s["exp_avg_sq"].copy_(ss["exp_avg_sq"])
