@@ -73,10 +73,10 @@ def main(argv=None):
     if on_gpu and not args.no_graph:
         from torchdistpackage_b200.ops.graph import GraphedStep
         ex = torch.zeros(args.micro_batch, model.cfg.seq_len, dtype=torch.long, device=dev)
-        # (capture after a resume: the graph replays kernels, the state they touch is already loaded)
-        # NOTE: the capture's warm-up iterations are real optimizer steps (on an all-zero batch);
-        # snapshot / restore the state around it if bit-exact step counts matter.
-        step_fn = GraphedStep(train_step, (ex, ex.clone()), warmup=2)
+        # the capture's warm-up iterations are real optimizer steps on an all-zero batch:
+        # `preserve` snapshots parameters + optimizer state (incl. the device step counter) around
+        # them, so a graph built after a resume continues exactly where the checkpoint left off
+        step_fn = GraphedStep(train_step, (ex, ex.clone()), warmup=2, preserve=opt.state_tensors())
 
     writer = AsyncCheckpointWriter()
     metrics = MetricsLogger(os.path.join(args.out, "metrics.jsonl"))

@@ -199,6 +199,58 @@ def test_zero_optimizer_matches_adam(bucket_size, overlap):
     run_distributed(_w_zero, 2, bucket_size, overlap)
 
 
+# ------------------------------------------------------------------ hybrid ZeRO (node-local shards)
+def _w_hybrid_zero(rank, world, mode, as_view, overlap):
+    """4 ranks = 2 "nodes" x 2: ZeRO shards inside the node, the cross-node average comes from
+    NaiveDDP (either construction order, world or inter-node group) or from ``outer_group``.
+    Every variant must track single-process Adam on the world-averaged loss."""
+    import torchdistpackage_b200 as tdp
+    tdp.fix_rand(0)
+    node = tdp.setup_node_groups(num_per_node=2)
+    inter = tdp.setup_inter_node_groups(num_per_node=2)
+    assert node is not None and inter is not None
+    model = nn.Sequential(nn.Linear(16, 32), nn.GELU(), nn.Linear(32, 7))
+    ref = copy.deepcopy(model)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    ddp = None
+    mk_ddp = lambda grp: tdp.NaiveDDP(model, process_group=grp, gradient_as_bucket_view=as_view,
+                                      bucket_cap_mb=0.001)
+    mk_zero = lambda **kw: tdp.Bf16ZeroOptimizer(torch.optim.Adam(model.parameters(), lr=1e-2),
+                                                 dp_group=node, overlap_comm=overlap,
+                                                 bucket_size=256, **kw)
+    if mode == "ddp_world_first":
+        ddp = mk_ddp(None); zopt = mk_zero()
+    elif mode == "ddp_inter_first":
+        ddp = mk_ddp(inter); zopt = mk_zero()
+    elif mode == "zero_first":
+        zopt = mk_zero(); ddp = mk_ddp(None)
+    else:
+        zopt = mk_zero(outer_group=inter)
+    fwd = ddp if ddp is not None else model
+    for it in range(4):
+        xs = []
+        for r in range(world):
+            torch.manual_seed(100 * it + r)
+            xs.append(torch.randn(6, 16) + r)
+        zopt.zero_grad()
+        fwd(xs[rank]).pow(2).sum().backward()
+        if ddp is not None:
+            ddp.reduce_gradients()
+        zopt.step()
+        ref_opt.zero_grad()
+        (sum(ref(x).pow(2).sum() for x in xs) / world).backward()
+        ref_opt.step()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (mode, it, (p - q).abs().max())
+
+
+@pytest.mark.parametrize("mode,as_view,overlap", [
+    ("ddp_world_first", True, True), ("ddp_world_first", False, False),
+    ("ddp_inter_first", True, True), ("zero_first", True, True), ("outer_group", True, True)])
+def test_hybrid_zero_matches_adam(mode, as_view, overlap):
+    run_distributed(_w_hybrid_zero, 4, mode, as_view, overlap)
+
+
 # ------------------------------------------------------------------ sharded EMA
 def _w_ema(rank, world):
     import torchdistpackage_b200 as tdp

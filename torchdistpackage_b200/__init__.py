@@ -10,7 +10,7 @@ from .ddp.zero_optim import Bf16ZeroOptimizer
 from .dist.launch import setup_distributed, find_free_port, get_cpu_group, shutdown_distributed
 from .dist.process_topo import torch_parallel_context as tpc
 from .dist.process_topo import torch_parallel_context, test_comm, is_using_pp, ProcessTopology
-from .dist.node_group import setup_node_groups
+from .dist.node_group import setup_node_groups, setup_inter_node_groups
 from .dist.sharded_ema import ShardedEMA
 from .dist.model_parallel_ckpt import get_mp_ckpt_suffix, save_mp_checkpoint, load_mp_checkpoint
 

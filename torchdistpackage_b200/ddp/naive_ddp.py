@@ -124,8 +124,24 @@ class _GradReducer:
         self._use_symm_req = use_symm
         self.buckets: List[GradBucket] = []
         self.param_bucket: Dict[str, GradBucket] = {}
+        self._claim_params()
         self._build_buckets()
         self._register_hooks()
+
+    def _claim_params(self) -> None:
+        """One owner for ``p.grad``: mark the parameters as reduced by this engine so a
+        ``Bf16ZeroOptimizer`` built later turns into a consumer of the reduced gradients, and tell
+        an optimizer built *earlier* to hand ownership over (hybrid ZeRO, ddp/zero_optim.py)."""
+        import weakref
+        me = weakref.ref(self)
+        for p in self.params.values():
+            if not p.requires_grad:
+                continue
+            zref = getattr(p, "_tdp_zero", None)
+            z = zref() if zref is not None else None
+            if z is not None:
+                z.attach_external_reducer(self)
+            p._tdp_reducer = me
 
     # ------------------------------------------------------------------ groups
     def _group_of(self, name: str, p: torch.nn.Parameter):
@@ -226,7 +242,7 @@ class _GradReducer:
             h.remove()
         self._hooks = []
         for p in self.params.values():
-            for attr in ("_tdp_main_grad", "_tdp_grad_fresh"):
+            for attr in ("_tdp_main_grad", "_tdp_grad_fresh", "_tdp_reducer"):
                 if hasattr(p, attr):
                     delattr(p, attr)
 
@@ -425,7 +441,14 @@ class NaiveDDP(torch.nn.Module):
         """Make every replica start from ``dp_rank0``'s parameters and buffers."""
         tensors = [t for n, t in self.module.state_dict().items()
                    if n not in self.parameters_to_ignore and torch.is_tensor(t)]
-        _GradReducer.broadcast_tensors(tensors, self.dp_rank0, self.group)
+        src = self.dp_rank0
+        if self.group is not None and dist.is_initialized():
+            # ``dp_rank0`` is a *global* rank (reference semantics, naive_ddp.py:226-230, which
+            # fails when global rank 0 is not a member); fall back to the group's first rank
+            ranks = dist.get_process_group_ranks(self.group)
+            if src not in ranks:
+                src = ranks[0]
+        _GradReducer.broadcast_tensors(tensors, src, self.group)
 
     def sync_comm(self) -> None:
         if self.reducer.on_cuda:

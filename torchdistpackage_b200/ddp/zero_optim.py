@@ -25,8 +25,19 @@ broadcast, zero_optim.py:73-95,282-287):
 * CPU / gloo fallback uses all_reduce + slice and ``dist.all_gather`` (tests, BASELINE config #1).
 * ``state_dict()`` / ``load_state_dict()`` exist (shard-local), which the reference lacks.
 
-Hybrid ZeRO: pass ``dp_group=setup_node_groups()`` and wrap the model in ``NaiveDDP`` over the
-inter-node group for the cross-node average (Intro.md:69-79 of the reference).
+Hybrid ZeRO (shard inside the node, replicate across nodes; Intro.md:69-79 and
+dist/node_group.py:13-19 of the reference) comes in two forms:
+
+* ``Bf16ZeroOptimizer(optim, dp_group=node_group, outer_group=inter_node_group)``: the in-node
+  reduce-scatter is followed by an all-reduce of *this rank's fp32 shard only* over the ranks
+  with the same local index on the other nodes -- 1/N of the gradient crosses the slow link.
+* the reference's documented composition, ``NaiveDDP(model)`` (over the world or the inter-node
+  group) plus ``Bf16ZeroOptimizer(dp_group=node_group)``: the optimizer detects the DDP reducer
+  on its parameters (either construction order) and becomes a pure *consumer*: ``p.grad`` stays
+  owned by NaiveDDP, no ZeRO hooks run during backward, and ``step()`` reads the gradients only
+  after ``reduce_gradients()`` has ordered the compute stream behind the DDP reductions.  If
+  the DDP group already covers the ZeRO group the shard is sliced out without any further
+  communication, otherwise the in-node reduce-scatter runs on the DDP-reduced values.
 """
 from __future__ import annotations
 
@@ -59,9 +70,14 @@ class Bf16ZeroOptimizer:
     def __init__(self, optim: torch.optim.Optimizer, dp_group=None,
                  bf16_master_weights: bool = False, overlap_comm: bool = False, stage: int = 2,
                  bucket_size: float = 5e8, bucketize: bool = True, use_symm: Optional[bool] = None,
-                 grad_acc_steps: int = 1):
+                 grad_acc_steps: int = 1, outer_group=None):
         self.optim = optim
         self.group = dp_group
+        self.outer_group = outer_group
+        self.outer_world = (dist.get_world_size(outer_group)
+                            if (outer_group is not None and dist.is_initialized()) else 1)
+        self._ext_reducers: list = []        # NaiveDDP reducers that own p.grad (hybrid mode)
+        self._ext_covers = False
         self.world = dist.get_world_size(dp_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(dp_group) if dist.is_initialized() else 0
         self.bf16_master_weights = bool(bf16_master_weights)
@@ -104,7 +120,43 @@ class Bf16ZeroOptimizer:
         self._build()
 
     # ------------------------------------------------------------------ construction
+    def _find_external_reducers(self) -> None:
+        seen = {}
+        for pg in self.optim.param_groups:
+            for p in pg["params"]:
+                ref = getattr(p, "_tdp_reducer", None)
+                r = ref() if ref is not None else None
+                if r is not None:
+                    seen[id(r)] = r
+        if seen:
+            self._set_external(list(seen.values()))
+
+    def _set_external(self, reducers: list) -> None:
+        self._ext_reducers = reducers
+        mine = set(dist.get_process_group_ranks(self.group)) if (
+            dist.is_initialized() and self.group is not None) else None
+        covers = True
+        for r in reducers:
+            g = r.default_group
+            if g is None or not dist.is_initialized():
+                continue                    # the world group covers everything
+            if mine is None or not mine <= set(dist.get_process_group_ranks(g)):
+                covers = False
+        self._ext_covers = covers
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    def attach_external_reducer(self, reducer) -> None:
+        """Called by NaiveDDP when it wraps a model whose parameters this optimizer already
+        manages: hand gradient ownership to the DDP engine (see module docstring)."""
+        if all(r is not reducer for r in self._ext_reducers):
+            self._set_external(self._ext_reducers + [reducer])
+
     def _build(self) -> None:
+        self._find_external_reducers()
+        import weakref
+        wself = weakref.ref(self)
         for gi, pg in enumerate(self.optim.param_groups):
             params = [p for p in pg["params"]]
             self.model_param_groups.append(params)
@@ -169,8 +221,10 @@ class Bf16ZeroOptimizer:
                     gview = flat_g[off:off + p.numel()].view(p.shape)
                     if p.grad is not None:
                         gview.copy_(p.grad)
-                    p.grad = gview if p.requires_grad else None
+                    if not self._ext_reducers:
+                        p.grad = gview if p.requires_grad else None
                     p._zero_grad_view = gview
+                    p._tdp_zero = wself
                     touched = [b for b in group_buckets
                                if b.start < off + p.numel() and off < b.start + b.numel]
                     self._param_bucket[id(p)] = touched
@@ -209,13 +263,16 @@ class Bf16ZeroOptimizer:
             self.master_grad.append(mgrad)
             pg["params"] = [master]
 
-        for params in self.model_param_groups:
-            for p in params:
-                if p.requires_grad:
-                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        if not self._ext_reducers:
+            for params in self.model_param_groups:
+                for p in params:
+                    if p.requires_grad:
+                        self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     # ------------------------------------------------------------------ backward hooks
     def _on_grad(self, p: torch.Tensor) -> None:
+        if self._ext_reducers:
+            return
         gview = p._zero_grad_view
         if p.grad is not None and p.grad.data_ptr() != gview.data_ptr():
             gview.copy_(p.grad)      # user dropped the view: re-attach
@@ -249,9 +306,12 @@ class Bf16ZeroOptimizer:
         gi = b.group_idx
         flat_g = self.flat_grad[gi]
         out = self._master_slice(b, self.master_grad[gi])
-        if self.world == 1:
+        if self.world == 1 or (self._ext_reducers and self._ext_covers):
+            # nothing to reduce inside the group (single rank, or NaiveDDP already averaged over a
+            # group that contains it): my shard is a slice of the local gradient
             if out.data_ptr() != self._slice_of(b, flat_g).data_ptr():
                 out.copy_(self._slice_of(b, flat_g))
+            self._outer_reduce(out)
             return
         sym = self.symm[gi]
         if self.on_cuda:
@@ -267,14 +327,45 @@ class Bf16ZeroOptimizer:
                     tmp = torch.empty(b.slice, dtype=seg.dtype, device=seg.device)
                     dist.reduce_scatter_tensor(tmp, seg, op=dist.ReduceOp.AVG, group=self.group)
                     out.copy_(tmp)
+                self._outer_reduce(out)
         else:
             seg = flat_g[b.start:b.start + b.numel]
             dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
             out.copy_(self._slice_of(b, flat_g))
             out.div_(self.world)
+            self._outer_reduce(out)
+
+    def _outer_reduce(self, shard: torch.Tensor) -> None:
+        """Hybrid ZeRO, ``outer_group`` form: average my shard with the same shard on the other
+        nodes (NCCL / gloo: this hop leaves the NVSwitch domain)."""
+        if self.outer_world <= 1:
+            return
+        if self.on_cuda:
+            dist.all_reduce(shard, op=dist.ReduceOp.AVG, group=self.outer_group)
+        else:
+            dist.all_reduce(shard, op=dist.ReduceOp.SUM, group=self.outer_group)
+            shard.div_(self.outer_world)
+
+    def _pull_external_grads(self) -> None:
+        """Hybrid mode: NaiveDDP owns ``p.grad``.  Make sure its reductions are finished and
+        ordered before this stream, then copy the reduced gradients into the flat layout."""
+        for r in self._ext_reducers:
+            if not r._finalized:
+                r.finalize()
+        with torch.no_grad():
+            for params in self.model_param_groups:
+                for p in params:
+                    if not p.requires_grad:
+                        continue
+                    if p.grad is None:
+                        p._zero_grad_view.zero_()
+                    elif p.grad.data_ptr() != p._zero_grad_view.data_ptr():
+                        p._zero_grad_view.copy_(p.grad)
 
     def finish_bucket(self) -> None:
         """Flush reductions that did not fire from the hooks (no overlap, unused params)."""
+        if self._ext_reducers and not all(b.reduced for b in self.buckets):
+            self._pull_external_grads()
         for b in self.buckets:
             self._reduce_bucket(b)
 
@@ -373,6 +464,14 @@ class Bf16ZeroOptimizer:
             g.zero_()
         for mg in self.master_grad:
             mg.zero_()
+        if self._ext_reducers:              # the model gradients live in NaiveDDP's buckets
+            for params in self.model_param_groups:
+                for p in params:
+                    if p.grad is not None:
+                        if set_to_none:
+                            p.grad = None
+                        else:
+                            p.grad.zero_()
 
     @property
     def state(self):

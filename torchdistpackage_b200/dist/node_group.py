@@ -36,3 +36,26 @@ def setup_node_groups(num_per_node: int = 8):
         if dist.get_rank() in ranks:
             mine = grp
     return mine
+
+
+def inter_node_rank_lists(world_size: int, num_per_node: int = 8) -> Optional[List[List[int]]]:
+    """Pure helper: for every local index, the ranks holding it on each node."""
+    if node_rank_lists(world_size, num_per_node) is None:
+        return None
+    return [list(range(i, world_size, num_per_node)) for i in range(num_per_node)]
+
+
+def setup_inter_node_groups(num_per_node: int = 8):
+    """The complementary axis of :func:`setup_node_groups`: one group per local index, joining
+    the ranks that hold the same ZeRO shard on different nodes (``Bf16ZeroOptimizer(...,
+    outer_group=...)`` or ``NaiveDDP(process_group=...)`` for hybrid ZeRO).  ``None`` on a
+    single node."""
+    lists = inter_node_rank_lists(dist.get_world_size(), num_per_node)
+    if lists is None:
+        return None
+    mine = None
+    for ranks in lists:
+        grp = dist.new_group(ranks)
+        if dist.get_rank() in ranks:
+            mine = grp
+    return mine

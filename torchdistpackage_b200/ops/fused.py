@@ -313,7 +313,32 @@ class BucketAdamW:
         for st in self.state:
             st["bucket"].buffer.zero_()
 
+    def set_lr(self, lr: float) -> None:
+        """Change the learning rate *outside* a captured step: the kernel reads lr from device
+        memory, so the next CUDA-graph replay picks it up (editing ``param_groups`` alone is only
+        seen by the Python ``step()``, which does not run during replay)."""
+        self.param_groups[0]["lr"] = float(lr)
+        if self._hyper is not None:
+            self._hyper[1].fill_(float(lr))
+            self._hyper_lr = float(lr)
+
+    def current_step(self) -> int:
+        """Number of optimizer steps taken, including CUDA-graph replays (device counter)."""
+        if self._hyper is not None:
+            return int(round(float(self._hyper[0].item())))
+        return self.step_count
+
+    def state_tensors(self) -> List[torch.Tensor]:
+        """Every tensor ``step()`` mutates (for ``GraphedStep(preserve=...)``)."""
+        out = [] if self._hyper is None else [self._hyper]
+        for st in self.state:
+            out += [st["flat_p"], st["exp_avg"], st["exp_avg_sq"]]
+            if st["master"] is not None:
+                out.append(st["master"])
+        return out
+
     def state_dict(self) -> dict:
+        self.step_count = self.current_step()      # replays advance only the device counter
         return dict(step=self.step_count, param_groups=[{k: v for k, v in g.items() if k != "params"}
                                                         for g in self.param_groups],
                     buckets=[dict(exp_avg=s["exp_avg"].cpu(), exp_avg_sq=s["exp_avg_sq"].cpu(),

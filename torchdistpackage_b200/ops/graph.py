@@ -26,9 +26,16 @@ class GraphedStep:
     memory (parameters, optimizer state).  The returned tensors are static: read them (``.item()``)
     before the next replay."""
 
-    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 3):
+    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 3,
+                 preserve: Sequence[torch.Tensor] = ()):
+        """``preserve``: tensors the step mutates (parameters, optimizer state -- e.g.
+        ``list(model.parameters()) + opt.state_tensors()``) that must come out of the warm-up
+        unchanged: they are snapshotted before the warm-up iterations (which are *real* steps on
+        the example inputs) and restored before capture, so building the graph after a
+        checkpoint resume does not advance the run."""
         assert torch.cuda.is_available()
         self.static_inputs = [t.clone() for t in example_inputs]
+        saved = [(t, t.detach().clone()) for t in preserve]
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -36,6 +43,10 @@ class GraphedStep:
             for _ in range(warmup):
                 fn(*self.static_inputs)
         cur.wait_stream(side)
+        with torch.no_grad():
+            for t, snap in saved:
+                t.copy_(snap)
+        del saved
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
