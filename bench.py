@@ -48,6 +48,11 @@ def parse_args():
     ap.add_argument("--micro-batch", type=int, default=MICRO_BATCH)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="ours: run the step eagerly")
+    ap.add_argument("--other-configs", default="auto", choices=["auto", "on", "off"],
+                    help="after the headline run, also time BASELINE configs #3/#4/#5 (both arms) "
+                         "outside the timed region; auto = only at --gpus 8")
+    ap.add_argument("--no-checks", action="store_true",
+                    help="skip the untimed gradient check / exposed-communication measurement")
     return ap.parse_args()
 
 
@@ -207,7 +212,131 @@ def build_ours(args, device, world):
         # a replay re-launches every captured kernel; the host-side counter does not see replays
         return replays["n"] * state["launches_per_replay"]
 
+    build_ours.ctx = dict(ddp=ddp, opt=opt, eager_step=eager_step, args=args)
     return counted_step, launches, model.cfg
+
+
+def grad_check_ours(step, batch, world, device):
+    """Untimed proof that the gradient the timed steps used is the data-parallel average.
+
+    One more step of the *timed* path (CUDA-graph replay, direct weight-gradient route into the
+    symmetric buckets, NVLS all-reduce kernels) on ``batch`` with lr = 0 (weights frozen); the
+    reduced buckets are kept.  Then the same batch runs through the eager step with the bucket
+    reduction disabled, which leaves every rank's *local* gradient in the buckets; those are
+    averaged with plain ``dist.all_reduce`` (NCCL) on a copy and compared."""
+    import torch.distributed as dist
+    ctx = build_ours.ctx
+    ddp, opt = ctx["ddp"], ctx["opt"]
+    red = ddp.reducer
+    lr0 = float(opt.param_groups[0]["lr"])
+    opt.set_lr(0.0)
+    tokens, targets = batch[:, :-1], batch[:, 1:]
+    step(tokens, targets)
+    torch.cuda.synchronize()
+    got = [b.payload().float().clone() for b in red.buckets]
+    orig = red._reduce_bucket
+    red._reduce_bucket = lambda bucket: setattr(bucket, "reduced", True)
+    try:
+        ctx["eager_step"](tokens.contiguous(), targets.contiguous())
+        torch.cuda.synchronize()
+    finally:
+        red._reduce_bucket = orig
+    worst_max, worst_l2, sym = 0.0, 0.0, 0
+    for b, g in zip(red.buckets, got):
+        ref = b.payload().float().clone()
+        dist.all_reduce(ref, group=b.group)
+        ref /= world
+        worst_max = max(worst_max, float((g - ref).abs().max() / ref.abs().max().clamp_min(1e-20)))
+        worst_l2 = max(worst_l2, float((g - ref).norm() / ref.norm().clamp_min(1e-20)))
+        sym += int(b.symm is not None)
+    opt.set_lr(lr0)
+    t = torch.tensor([worst_max, worst_l2], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"grad_check_rel": float(t[0]), "grad_check_rel_l2": float(t[1]),
+            "grad_check_buckets": len(red.buckets), "grad_check_symmetric_buckets": sym,
+            "grad_check_how": "graph-replayed step (direct wgrad -> NVLS all-reduce) vs local "
+                              "grads averaged by NCCL all_reduce, same batch, lr=0; max over "
+                              "buckets and ranks of max|diff|/max|ref| and of the L2 ratio"}
+
+
+def exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms_with_comm):
+    """BASELINE metric, second half: communication left exposed after overlap = step time with
+    the bucket all-reduces minus the time of the identical step with the collective skipped
+    (a second CUDA graph captured with the reduction disabled; everything else identical)."""
+    from torchdistpackage_b200.ops.graph import GraphedStep
+    ctx = build_ours.ctx
+    red = ctx["ddp"].reducer
+    orig = red._reduce_bucket
+    red._reduce_bucket = lambda bucket: setattr(bucket, "reduced", True)
+    try:
+        b0 = dev_batches[0]
+        if ctx["args"].no_graph:
+            g = ctx["eager_step"]
+        else:
+            g = GraphedStep(ctx["eager_step"], (b0[:, :-1], b0[:, 1:]), warmup=2)
+        for i in range(3):
+            b = dev_batches[i % len(dev_batches)]
+            g(b[:, :-1], b[:, 1:])
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(K):
+            b = dev_batches[i % len(dev_batches)]
+            g(b[:, :-1], b[:, 1:])
+        e.record()
+        barrier()
+        ms = max_over_ranks(s.elapsed_time(e)) / K
+    finally:
+        red._reduce_bucket = orig
+    del g
+    return {"exposed_comm_ms": ms_with_comm - ms, "ms_per_step_without_collective": ms}
+
+
+OTHER_CONFIGS = [
+    ("tp", "scripts/bench_tp.py", "#3 4-layer transformer h=4096 TP=N + SP"),
+    ("moe", "scripts/bench_moe.py", "#4 MoE 8-expert transformer EP x moe-DP"),
+    ("mixed", "scripts/bench_mixed.py", "#5 GPT-2 medium DP x PP=2 x TP=2 + SP, ZeRO, 1F1B"),
+]
+
+
+def run_other_configs(rank, world):
+    """BASELINE configs #3 / #4 / #5, both arms, each as a fresh set of ``world`` processes (this
+    rank spawns its counterpart with the same RANK / LOCAL_RANK on a new rendezvous port), timed by
+    the scripts themselves (CUDA events, max over ranks) -- outside the headline timed region.
+    Returns {name: {ours_ms, reference_ms, ratio, ...}} on rank 0."""
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    out = {}
+    idx = 0
+    for name, script, title in OTHER_CONFIGS:
+        if name == "mixed" and world % 4 != 0:
+            continue
+        rec = {"config": title}
+        for impl in ("reference", "ours"):
+            idx += 1
+            env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
+            env["MASTER_PORT"] = str(base_port + 100 + idx)
+            env["MASTER_ADDR"] = "127.0.0.1"
+            res = None
+            try:
+                cp = subprocess.run([sys.executable, os.path.join(ROOT, script), "--impl", impl],
+                                    env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                    text=True, timeout=240)
+                for ln in cp.stdout.splitlines():
+                    if ln.startswith("{"):
+                        res = json.loads(ln)
+                if res is None and rank == 0:
+                    rec[impl + "_error"] = (cp.stderr or "")[-300:]
+            except Exception as ex:       # a failed side config must not take the headline down
+                if rank == 0:
+                    rec[impl + "_error"] = f"{type(ex).__name__}: {ex}"[:300]
+            if res is not None:
+                rec[impl + "_ms_per_step"] = res["ms_per_step"]
+                rec[impl + "_tokens_per_s"] = res["tokens_per_s"]
+                rec["shape"] = res.get("config", title) if impl == "ours" else rec.get("shape", res.get("config"))
+        if "ours_ms_per_step" in rec and "reference_ms_per_step" in rec:
+            rec["ratio"] = rec["reference_ms_per_step"] / rec["ours_ms_per_step"]
+        out[name] = rec
+    return out
 
 
 _REAL_STDOUT_FD = None
@@ -339,6 +468,30 @@ def main():
                "d2h_bytes_per_step": 4}
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- untimed extras (ours arm): exposed communication, gradient proof
+    extras = {}
+    if args.impl == "ours" and world > 1 and not args.no_checks:
+        try:
+            extras.update(exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms / K))
+        except Exception as ex:
+            extras["exposed_comm_error"] = f"{type(ex).__name__}: {ex}"[:200]
+        try:
+            extras.update(grad_check_ours(step, dev_batches[0], world, device))
+        except Exception as ex:
+            extras["grad_check_error"] = f"{type(ex).__name__}: {ex}"[:200]
+    do_other = args.other_configs == "on" or (args.other_configs == "auto" and world == 8)
+    if do_other and world > 1 and args.impl == "ours":
+        barrier()
+        dist.destroy_process_group()
+        build_ours.ctx = None
+        torch.cuda.empty_cache()
+        other = run_other_configs(rank, world)
+        if rank == 0:
+            extras["other_configs"] = other
+        world_done = True
+    else:
+        world_done = False
+
     if rank == 0:
         tokens_per_s = world * B * S * K / (ms / 1e3)
         try:
@@ -364,8 +517,9 @@ def main():
             "final_loss": final_loss,
             "model_flops_utilization_of_measured_cublas": mfu,
         }
+        out.update(extras)
         emit_json(out)
-    if world > 1:
+    if world > 1 and not world_done:
         dist.barrier()
         dist.destroy_process_group()
 

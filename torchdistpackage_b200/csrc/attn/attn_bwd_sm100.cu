@@ -1,24 +1,27 @@
-// Flash-attention backward for sm_100a (companion of attn_fwd_sm100.cu, same layout contract).
+// Flash-attention backward, key/value-gradient half, for sm_100a (companion of
+// attn_bwd_dq_sm100.cu, which runs first and produces dQ and delta; same layout contract as the
+// forward kernel).
 //
 // One CTA owns one 128-key tile (b, h, j) and walks the query tiles i that see it:
 //     S   = Q_i K_j^T                 UMMA 128x128x64  -> TMEM [  0,128)
 //     dP  = dO_i V_j^T                UMMA 128x128x64  -> TMEM [128,256)
-//     softmax warp-group (thread = query row):  P = exp2(S c - lse),  dS = scale P (dP - delta)
-//                                     -> bf16 P and dS tiles in swizzled smem (double buffered)
+//     two softmax warp-groups (thread = query row, warp-group = 64-key half of the tile):
+//         P = exp2(S c - lse),  dS = P (dP - delta)   -> bf16 P and dS tiles in swizzled smem
+//                                                        (double buffered)
 //     dV += P^T  dO_i                 UMMA 128x64x128  -> TMEM [256,320)   accumulated over i
 //     dK += dS^T Q_i                  UMMA 128x64x128  -> TMEM [320,384)   accumulated over i
-//     dQ_i = dS  K_j                  UMMA 128x64x128  -> TMEM [384,448)
-//     drain warp-group: dQ_i tile -> red.global.add.v4.f32 into the fp32 dQ accumulator
-//   end: dK, dV -> bf16 -> swizzled smem -> TMA store.
+//   end: dV, scale * dK -> bf16 -> swizzled smem -> TMA store (into the k / v windows of the packed
+//   dqkv gradient).
 //
 // Every smem tile is used through two descriptor views without ever being transposed:
 //   Q_i / dO_i / K_j  [128 rows x 64]   as K-major A/B (rows = M/N) and as MN-major B (rows = K)
-//   P / dS  stored as [key half][q half][64 q][64 keys] boxes: K-major A for dS K (SBO 1 KiB, the
-//   two q halves adjacent) and MN-major A for P^T dO / dS^T Q (LBO = 16 KiB between key halves).
+//   P / dS  stored as [key half][q half][64 q][64 keys] boxes, read as MN-major A for P^T dO /
+//   dS^T Q (LBO = 16 KiB between key halves).
 //
-//   warp 0  TMA producer     warp 1  MMA issuer + TMEM     warps 2-5  softmax WG   warps 6-9  dQ drain
+//   warps 0-3 / 4-7  softmax warp-groups (key half 0 / 1)    warp 8  TMA producer
+//   warp 9  MMA issuer + TMEM allocation                      warps 10-11 idle (setmaxnreg group)
 //
-// STATUS: not yet run on hardware (see attn_fwd_sm100.cu); opt-in, checked by scripts/attn_check.py.
+// Validated on B200 by scripts/attn_check.py and tests/test_gpu_kernels.py.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,6 +31,7 @@
 #include "../common/ptx.cuh"
 #include "../common/tdp_api.h"
 #include "../common/tmap.h"
+#include "attn_common.cuh"
 
 namespace tdp {
 
@@ -38,7 +42,7 @@ constexpr int kT = 128;                       // tile edge (queries and keys)
 constexpr int kTile = kT * kD * 2;            // 16 KiB  [128 x 64] bf16
 constexpr int kPTile = kT * kT * 2;           // 32 KiB  [128 x 128] bf16
 constexpr int kQStages = 2;
-constexpr int kBwdThreads = 32 * 10;
+constexpr int kBwdThreads = 32 * 12;
 constexpr uint32_t kBwdTmemCols = 512;
 
 struct BwdSmem {
@@ -55,16 +59,10 @@ struct BwdParams {
   int causal;
   float scale, scale_log2;
   const float* lse;        // [B, H, T] natural log
-  const float* delta;      // [B, H, T] rowsum(dO * O)
-  float* dq_acc;           // fp32 [B*T, H*64], zero-initialised
+  const float* delta;      // [B, H, T] rowsum(dO * O)  (written by the dQ kernel)
 };
 
-TDP_DEVICE float ex2b(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-TDP_DEVICE void bar_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+using namespace attn;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,128}
@@ -87,9 +85,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
   uint64_t* s_full = q_empty + kQStages;         // S_i and dP_i ready
   uint64_t* p_ready = s_full + 1;                // 2 (per P/dS buffer): written, S/dP consumed
   uint64_t* pds_free = p_ready + 2;              // 2: the MMAs reading buffer u have completed
-  uint64_t* dq_full = pds_free + 2;              // dQ_i tile ready
-  uint64_t* dq_free = dq_full + 1;               // drain group has read it
-  uint64_t* dkv_full = dq_free + 1;              // all of dK / dV accumulated
+  uint64_t* dkv_full = pds_free + 2;             // all of dK / dV accumulated
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dkv_full + 1);
 
   const int warp_idx = threadIdx.x / 32;
@@ -100,7 +96,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
   const int n_iter = n_tiles - i0;
   const int row_base = b * p.T;
 
-  if (warp_idx == 0 && elect_one()) {
+  if (warp_idx == 8 && elect_one()) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -112,23 +108,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
     }
     mbar_init(s_full, 1);
     for (int u = 0; u < 2; ++u) {
-      mbar_init(&p_ready[u], 4);
+      mbar_init(&p_ready[u], 8);               // one elected lane per softmax warp (2 groups)
       mbar_init(&pds_free[u], 1);
     }
-    mbar_init(dq_full, 1);
-    mbar_init(dq_free, 4);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == 9) {
     tmem_alloc<kBwdTmemCols>(tmem_holder);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+  constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320;
 
-  if (warp_idx == 0) {
+  if (warp_idx >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp_idx == 8) {
     // ================================ TMA producer ================================
     if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * kTile);
@@ -144,7 +140,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
                     row_base + (i0 + it) * kT);
       }
     }
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == 9) {
     // ================================ MMA issuer ================================
     const uint32_t idesc_s = make_idesc_bf16_f32(kT, kT, 0, 0);     // A K-major, B K-major, N=128
     const uint32_t idesc_t = make_idesc_bf16_f32(kT, kD, 1, 1);     // A^T (MN-major), B MN-major
@@ -171,19 +167,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
         }
       }
     };
-    // C[128 q x 64] = dS[128 q x 128 keys] K_j[128 keys x 64]: A K-major (2 key halves), B MN-major
-    auto mma_nn = [&](uint32_t col, uint32_t sx, uint32_t sy) {
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_umma_smem_desc_sw128(sx + kb * kTile + k * 32, 0, 1024);
-          const uint64_t db = make_umma_smem_desc_sw128(sy + kb * (kTile / 2) + k * 16 * 128, kTile / 2, 1024);
-          umma_f16_ss(tmem_base + col, da, db, idesc_q, (kb | k) != 0 ? 1u : 0u);
-        }
-      }
-    };
-
     mbar_wait(kv_full, 0);
     if (n_iter > 0) {
       mbar_wait(&q_full[0], 0);
@@ -213,25 +196,22 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
         }
         __syncwarp();
       }
-      if (it > 0) {
-        mbar_wait(dq_free, (it - 1) & 1);                       // previous dQ tile drained
-        tc_fence_after();
-      }
       if (elect_one()) {
         mma_tn(kColDV, sp, sdo, it > 0);                        // dV += P^T dO_i
         mma_tn(kColDK, sds, sq, it > 0);                        // dK += dS^T Q_i
-        mma_nn(kColDQ, sds, sk);                                // dQ_i = dS K_j
-        umma_commit(dq_full);
         umma_commit(&pds_free[u]);
         umma_commit(&q_empty[s]);
         if (it == n_iter - 1) umma_commit(dkv_full);
       }
       __syncwarp();
     }
-  } else if (warp_idx < 6) {
-    // ================================ softmax warp-group ================================
+   }
+  } else {
+    // ================================ softmax warp-groups ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int wg = warp_idx >> 2;                      // key half handled by this warp-group
     const int quad = warp_idx & 3;
-    const int row = quad * 32 + lane;
+    const int row = quad * 32 + lane;                  // query row in the tile = TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int swz = row & 7;
     const float* lse_bh = p.lse + (static_cast<size_t>(b) * p.H + h) * p.T;
@@ -240,118 +220,81 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
       const int i = i0 + it, u = it & 1;
       const float lse2 = lse_bh[i * kT + row] * 1.4426950408889634f;
       const float dlt = delta_bh[i * kT + row];
-      const bool diag = p.causal && (i == j);
       uint8_t* pbuf = smem_pds + u * 2 * kPTile;
       uint8_t* dsbuf = pbuf + kPTile;
-      if (it >= 2) mbar_wait(&pds_free[u], ((it - 2) >> 1) & 1);   // buffer u no longer read
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      uint32_t rs[64], rp[64];
+      tmem_ld_x32_at(tmem_base + kColS + wg * 64 + lane_off, rs);
+      tmem_ld_x32_at(tmem_base + kColS + wg * 64 + 32 + lane_off, rs + 32);
+      tmem_ld_x32_at(tmem_base + kColDP + wg * 64 + lane_off, rp);
+      tmem_ld_x32_at(tmem_base + kColDP + wg * 64 + 32 + lane_off, rp + 32);
+      tmem_ld_wait();
+      // causal diagonal tile (i == j): key wg*64 + e is visible to query `row` iff <= row
+      const int lim = (p.causal && i == j) ? (row - wg * 64) : 64;
+      uint32_t pp[32], dd[32];
 #pragma unroll
-      for (int c = 0; c < kT / 32; ++c) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32b_x32(tmem_base + kColS + c * 32 + lane_off, rs);
-        tmem_ld_32x32b_x32(tmem_base + kColDP + c * 32 + lane_off, rp);
-        tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+      for (int e = 0; e < 64; e += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
+        float p1 = ex2(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2));
+        if (e > lim) p0 = 0.f;
+        if (e + 1 > lim) p1 = 0.f;
+        pp[e / 2] = pack_bf16x2(p0, p1);
+        dd[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - dlt),
+                                p1 * (__uint_as_float(rp[e + 1]) - dlt));
+      }
+      // S / dP of this tile are in registers; the buffer may still be read by the MMAs of it-2
+      if (it >= 2) mbar_wait(&pds_free[u], ((it - 2) >> 1) & 1);
+      // key half wg; box (key half, q half) = rows of 128 B
+      const int off = wg * kTile + row * 128;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = ex2b(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
-          float p1 = ex2b(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2));
-          if (diag) {
-            if (c * 32 + e > row) p0 = 0.f;
-            if (c * 32 + e + 1 > row) p1 = 0.f;
-          }
-          const float d0 = p.scale * p0 * (__uint_as_float(rp[e]) - dlt);
-          const float d1 = p.scale * p1 * (__uint_as_float(rp[e + 1]) - dlt);
-          pp[e / 2] = pack_bf16x2(p0, p1);
-          dd[e / 2] = pack_bf16x2(d0, d1);
-        }
-        // keys [32c, 32c+32): key half c/2; box (key half, q half) = rows of 128 B
-        const int off = (c >> 1) * kTile + row * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (((c & 1) * 4 + q4) ^ swz) << 4;
-          *reinterpret_cast<uint4*>(pbuf + off + chunk) =
-              make_uint4(pp[4 * q4], pp[4 * q4 + 1], pp[4 * q4 + 2], pp[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(dsbuf + off + chunk) =
-              make_uint4(dd[4 * q4], dd[4 * q4 + 1], dd[4 * q4 + 2], dd[4 * q4 + 3]);
-        }
+      for (int c = 0; c < 8; ++c) {
+        const int chunk = (c ^ swz) << 4;
+        *reinterpret_cast<uint4*>(pbuf + off + chunk) =
+            make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        *reinterpret_cast<uint4*>(dsbuf + off + chunk) =
+            make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[u]);
     }
-    // ---- dK, dV accumulators -> bf16 -> swizzled staging (the Q / dO stages are idle now) -> TMA
+    // ---- accumulators -> bf16 -> swizzled staging (the Q / dO stages are idle now) -> TMA:
+    //      warp-group 0 writes dV, warp-group 1 writes scale * dK (thread = key row)
     if (n_iter > 0) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
-      uint8_t* stage_dv = smem_q;                 // 16 KiB each
-      uint8_t* stage_dk = smem_q + kTile;
+      uint8_t* stage = smem_q + wg * kTile;           // 16 KiB each
+      const uint32_t col = wg == 0 ? kColDV : kColDK;
+      const float mul = wg == 0 ? 1.f : p.scale;
+      uint32_t r[kD];
+      tmem_ld_x32_at(tmem_base + col + lane_off, r);
+      tmem_ld_x32_at(tmem_base + col + 32 + lane_off, r + 32);
+      tmem_ld_wait();
+      uint8_t* dst = stage + row * 128;
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        uint8_t* dst = (which == 0 ? stage_dv : stage_dk) + row * 128;
-        const uint32_t col = which == 0 ? kColDV : kColDK;
-#pragma unroll
-        for (int c = 0; c < kD / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_base + col + c * 32 + lane_off, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(r[8 * q4]), __uint_as_float(r[8 * q4 + 1]));
-            v.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]), __uint_as_float(r[8 * q4 + 3]));
-            v.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]), __uint_as_float(r[8 * q4 + 5]));
-            v.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]), __uint_as_float(r[8 * q4 + 7]));
-            *reinterpret_cast<uint4*>(dst + (((c * 4 + q4) ^ swz) << 4)) = v;
-          }
-        }
+      for (int c = 0; c < 8; ++c) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r[8 * c]) * mul, __uint_as_float(r[8 * c + 1]) * mul);
+        v.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul);
+        v.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul);
+        v.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul);
+        *reinterpret_cast<uint4*>(dst + ((c ^ swz) << 4)) = v;
       }
       fence_proxy_async_smem();
-      bar_sync_128(1);
-      if (warp_idx == 2 && lane == 0) {
-        tma_store_2d(&tmap_dv, stage_dv, h * kD, row_base + j * kT);
-        tma_store_2d(&tmap_dk, stage_dk, h * kD, row_base + j * kT);
+      wg_bar_sync(wg);
+      if (quad == 0 && lane == 0) {
+        tma_store_2d(wg == 0 ? &tmap_dv : &tmap_dk, stage, h * kD, row_base + j * kT);
         tma_store_commit();
         tma_store_wait<0>();
-      }
-    }
-  } else {
-    // ================================ dQ drain warp-group ================================
-    const int quad = warp_idx & 3;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const size_t ldq = static_cast<size_t>(p.H) * kD;
-    for (int it = 0; it < n_iter; ++it) {
-      const int i = i0 + it;
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      float* dst = p.dq_acc + (static_cast<size_t>(row_base) + i * kT + row) * ldq + h * kD;
-#pragma unroll
-      for (int c = 0; c < kD / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + kColDQ + c * 32 + lane_off, r);
-        tmem_ld_wait();
-        if (c == kD / 32 - 1) {
-          // all of the tile is in registers: let the next dQ MMA overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_free);
-        }
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c * 32 + e),
-                       "f"(__uint_as_float(r[e])), "f"(__uint_as_float(r[e + 1])),
-                       "f"(__uint_as_float(r[e + 2])), "f"(__uint_as_float(r[e + 3]))
-                       : "memory");
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) {
+  if (warp_idx == 9) {
     tc_fence_after();
     tmem_dealloc<kBwdTmemCols>(tmem_base);
   }
@@ -359,7 +302,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
 
 }  // namespace
 
-int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** err) {
+int launch_attn_bwd_dkv(const AttnBwdLaunch& a, cudaStream_t stream, const char** err) {
   static thread_local char msg[192];
   *err = msg;
   msg[0] = 0;
@@ -395,7 +338,7 @@ int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** er
   p.causal = a.causal;
   p.scale = a.scale;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  p.lse = a.lse; p.delta = a.delta; p.dq_acc = a.dq_acc;
+  p.lse = a.lse; p.delta = a.delta;
   dim3 grid(a.T / kT, a.H, a.B);
   attn_bwd_sm100_kernel<<<grid, kBwdThreads, BwdSmem::kTotal, stream>>>(tq, tk, tv, tdo, tdk, tdv, p);
   cudaError_t e = cudaGetLastError();
@@ -404,6 +347,12 @@ int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** er
     return static_cast<int>(e);
   }
   return 0;
+}
+
+int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** err) {
+  const int rc = launch_attn_bwd_dq(a, stream, err);
+  if (rc != 0) return rc;
+  return launch_attn_bwd_dkv(a, stream, err);
 }
 
 }  // namespace tdp

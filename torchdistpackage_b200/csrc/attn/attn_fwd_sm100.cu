@@ -1,28 +1,36 @@
-// Flash-attention forward for sm_100a: tcgen05.mma with S and the per-tile P.V product in TMEM,
-// TMA-fed K / V ring, two softmax warp-groups ping-ponging on two 128-row query tiles so the
-// tensor core works on one tile's QK^T / PV while the other tile's exponentials are computed.
+// Flash-attention forward for sm_100a: persistent, warp-specialised, tcgen05.mma with S *and* the
+// running output O in TMEM, TMA-fed K / V ring, two softmax warp-groups (one 128-row query tile
+// each) ping-ponging on the tensor core, lazy (thresholded) online-softmax rescaling.
 //
-//   warp 0          TMA producer  (Q tiles once; K(j), V(j) through a 3-stage ring each)
-//   warp 1          MMA issuer    (one elected thread) + TMEM allocation
-//   warps 2-5       softmax warp-group 0: query rows q0 .. q0+127      (thread = row = TMEM lane)
-//   warps 6-9       softmax warp-group 1: query rows q0+128 .. q0+255
+//   warps 0-3    softmax warp-group 0: query rows q0 .. q0+127      (thread = row = TMEM lane)
+//   warps 4-7    softmax warp-group 1: query rows q0+128 .. q0+255
+//   warp  8      TMA producer  (Q tiles per work item; K(j), V(j) through a 3-stage ring each)
+//   warp  9      MMA issuer    (one elected thread) + TMEM allocation
+//   warps 10-11  idle (they only exist so that warps 8-11 form a warp-group for setmaxnreg:
+//                the two softmax groups run with 224 registers, the rest with 56)
+//
+//   work item = (batch b, head h, 256 query rows); one CTA per SM walks a static, heavy-first
+//   "snake" schedule over all items (causal tiles differ 5x in work), so set-up cost (TMEM
+//   allocation, barrier init, tensor-map prefetch) is paid once per SM, not once per tile, and the
+//   TMA / MMA warps run ahead into the next item while the softmax groups finish the current one.
 //
 //   per KV tile j and warp-group w:
-//     S_w = Q_w K_j^T            UMMA 128x128x64   -> TMEM cols [128w, 128w+128)
-//     WG w: row max, online-softmax rescale, P = exp2(S*c - m) -> bf16 -> swizzled smem (A operand)
-//     O_w' = P_w V_j             UMMA 128x64x128   -> TMEM cols [256+64w, ...)   (not accumulated)
-//     WG w: o = (o + O_w') * alpha   in registers (fp32), l likewise
-//   epilogue: o / l -> bf16 -> swizzled smem -> TMA store; LSE (natural log) -> global.
+//     S_w  = Q_w K_j^T           UMMA 128x128x64   -> TMEM cols [128w, 128w+128)
+//     WG w: one TMEM read of the whole 128-column row, row max; the running max m is only
+//           advanced (and O_w / l rescaled, in TMEM) when the new max exceeds it by > 2^8 --
+//           rare after the first tile, so the O correction is off the critical path
+//           P = exp2(S*c - m) -> bf16 -> swizzled smem (A operand)
+//     O_w += P_w V_j             UMMA 128x64x128   -> TMEM cols [256+64w, ...)  (accumulated)
+//   end of item: O_w / l -> bf16 -> swizzled smem -> TMA store; LSE (natural log) -> global.
 //
 // Layout contract: q, k, v, o are [B*T, ld] row-major "token matrices" whose row r = b*T + t holds
 // all heads of a token (head h at columns col0 + h*64 ...): exactly the packed qkv GEMM output
 // (q | k | v along the row) and the [B, T, H*D] attention output -- no permutes, no split copies.
 // head_dim = 64, T % 128 == 0.
 //
-// STATUS: written against the same descriptor / barrier building blocks as the GEMM kernels
-// (which are validated on B200); this kernel itself has not run on hardware yet -- it is opt-in
-// (TDP_ATTN=native) and checked by scripts/attn_check.py.  (reference: attn.py:40-43 is the
-// unfused QK^T / softmax / PV this replaces.)
+// Validated on B200 by scripts/attn_check.py and tests/test_gpu_kernels.py (vs an fp32 dense
+// reference).  (reference: parallel/tensor_parallel/attn.py:40-43 is the unfused QK^T / softmax /
+// PV this replaces; explore/flash-attn/tile_attn.py:100-212 is the tiled algorithm.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -32,6 +40,7 @@
 #include "../common/ptx.cuh"
 #include "../common/tdp_api.h"
 #include "../common/tmap.h"
+#include "attn_common.cuh"
 
 namespace tdp {
 
@@ -41,10 +50,11 @@ constexpr int kHeadDim = 64;
 constexpr int kTileQ = 128;          // query rows per warp-group
 constexpr int kTileKV = 128;         // keys per iteration
 constexpr int kStagesKV = 3;
-constexpr int kAttnThreads = 32 * 10;
+constexpr int kAttnThreads = 32 * 12;
 constexpr int kTileBytes = kTileQ * kHeadDim * 2;        // 16 KiB: one [128 x 64] bf16 tile
 constexpr int kPBytes = kTileQ * kTileKV * 2;            // 32 KiB: P tile, two K-major k-blocks
-constexpr uint32_t kTmemColsAttn = 512;                  // S0 | S1 | O0' | O1' (384 used)
+constexpr uint32_t kTmemColsAttn = 512;                  // S0 | S1 | O0 | O1 (384 used)
+constexpr float kRescaleThreshold = 8.f;                 // log2 units
 
 struct AttnSmem {
   static constexpr int kQ = 0;                                   // 2 tiles
@@ -59,22 +69,36 @@ struct AttnParams {
   int B, T, H;
   int causal;
   float scale_log2;        // softmax scale * log2(e)
-  int q_col0, k_col0, v_col0, o_col0;   // first column of head 0 in the respective token matrix
+  int n_qp;                // 256-row query blocks per (b, h)
+  int n_items;             // B * H * n_qp
   float* lse;              // [B, H, T]
 };
 
-TDP_DEVICE float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-TDP_DEVICE float lg2(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-TDP_DEVICE void wg_bar_sync(int wg) {
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+using namespace attn;
+
+// Static schedule shared by all roles: items are ordered heavy-first (for causal attention the
+// last query block of every (b, h) first), CTA c takes position c of even rounds and position
+// G-1-c of odd rounds ("snake"), which evens out the 5x spread in item weight.
+struct Item {
+  int b, h, q0;
+  int n_kv[2];
+  int n_max;
+};
+TDP_DEVICE bool get_item(const AttnParams& p, int round, Item& it) {
+  const int G = static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
+  const int idx = round * G + ((round & 1) ? (G - 1 - c) : c);
+  if (idx >= p.n_items) return false;
+  const int bh_count = p.B * p.H;
+  const int qp = p.n_qp - 1 - idx / bh_count;
+  const int bh = idx - (idx / bh_count) * bh_count;
+  it.b = bh / p.H;
+  it.h = bh - it.b * p.H;
+  it.q0 = qp * 2 * kTileQ;
+  const int n_all = p.T / kTileKV;
+  it.n_kv[0] = p.causal ? (it.q0 / kTileKV + 1) : n_all;
+  it.n_kv[1] = (it.q0 + kTileQ < p.T) ? (p.causal ? (it.q0 / kTileKV + 2) : n_all) : 0;
+  it.n_max = it.n_kv[0] > it.n_kv[1] ? it.n_kv[0] : it.n_kv[1];
+  return true;
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -91,34 +115,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
   uint8_t* smem_p = smem + AttnSmem::kP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::kBars);
   uint64_t* q_full = bars;                       // 1
-  uint64_t* k_full = bars + 1;                   // kStagesKV
+  uint64_t* q_empty = bars + 1;                  // 1: every S MMA of the item has completed
+  uint64_t* k_full = bars + 2;                   // kStagesKV
   uint64_t* k_empty = k_full + kStagesKV;
   uint64_t* v_full = k_empty + kStagesKV;
   uint64_t* v_empty = v_full + kStagesKV;
   uint64_t* s_full = v_empty + kStagesKV;        // 2: S_w ready for warp-group w
-  uint64_t* p_ready = s_full + 2;                // 2: P_w written (and S_w / O_w' consumed)
-  uint64_t* o_full = p_ready + 2;                // 2: O_w' = P_w V ready
+  uint64_t* p_ready = s_full + 2;                // 2: P_w written (and S_w consumed, O_w consistent)
+  uint64_t* o_full = p_ready + 2;                // 2: O_w += P_w V complete
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
-  // heavier (later, for causal) query tiles first
-  const int qpair = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qpair * 2 * kTileQ;                       // first query row of this CTA
-  const int row_base = b * p.T;                            // row of (b, t = 0) in the token matrices
-  // number of KV tiles each warp-group needs
-  const int n_all = p.T / kTileKV;
-  int n_kv[2];
-  n_kv[0] = p.causal ? (q0 / kTileKV + 1) : n_all;
-  n_kv[1] = (q0 + kTileQ < p.T) ? (p.causal ? (q0 / kTileKV + 2) : n_all) : 0;
-  const int n_max = n_kv[0] > n_kv[1] ? n_kv[0] : n_kv[1];
 
-  if (warp_idx == 0 && elect_one()) {
+  if (warp_idx == 8 && elect_one()) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < kStagesKV; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -131,7 +147,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
       mbar_init(&o_full[w], 1);
     }
     fence_barrier_init();
-  } else if (warp_idx == 1) {
+  } else if (warp_idx == 9) {
     tmem_alloc<kTmemColsAttn>(tmem_holder);
   }
   tc_fence_before();
@@ -139,221 +155,260 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp_idx == 0) {
-    // ================================ TMA producer ================================
-    if (elect_one()) {
-      const int n_q = n_kv[1] > 0 ? 2 : 1;
-      mbar_expect_tx(q_full, n_q * kTileBytes);
-      for (int w = 0; w < n_q; ++w)
-        tma_load_2d(&tmap_q, q_full, smem_q + w * kTileBytes, p.q_col0 + h * kHeadDim,
-                    row_base + q0 + w * kTileQ);
-      for (int j = 0; j < n_max; ++j) {
-        const int st = j % kStagesKV;
-        const uint32_t ph = (j / kStagesKV) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        tma_load_2d(&tmap_k, &k_full[st], smem_k + st * kTileBytes, p.k_col0 + h * kHeadDim,
-                    row_base + j * kTileKV);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        // one [128 keys x 64 d] box: rows of 128 B, i.e. two stacked [64 x 64] boxes -- exactly the
-        // MN-major B operand of P.V (one 8 KiB box per 64-key k-block)
-        tma_load_2d(&tmap_v, &v_full[st], smem_v + st * kTileBytes, p.v_col0 + h * kHeadDim,
-                    row_base + j * kTileKV);
-      }
-    }
-  } else if (warp_idx == 1) {
-    // ================================ MMA issuer ================================
-    // S = Q K^T : A = Q  [128 x 64]  K-major,  B = K [128 keys x 64] K-major   (N = 128)
-    // O'= P V   : A = P  [128 x 128] K-major (2 k-blocks), B = V [128 keys x 64] MN-major (N = 64)
-    const uint32_t idesc_s = make_idesc_bf16_f32(kTileQ, kTileKV, 0, 0);
-    const uint32_t idesc_o = make_idesc_bf16_f32(kTileQ, kHeadDim, 0, 1);
-    constexpr uint32_t kUmmaKBytes = 16 * 2;          // K = 16 bf16 along a 128-byte swizzled row
-    auto issue_s = [&](int w, int st) {
-      const uint32_t sa = smem_u32(smem_q + w * kTileBytes);
-      const uint32_t sb = smem_u32(smem_k + st * kTileBytes);
-#pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k) {
-        const uint64_t da = make_umma_smem_desc_sw128(sa + k * kUmmaKBytes, 0, 1024);
-        const uint64_t db = make_umma_smem_desc_sw128(sb + k * kUmmaKBytes, 0, 1024);
-        umma_f16_ss(tmem_base + w * kTileKV, da, db, idesc_s, k != 0 ? 1u : 0u);
-      }
-      umma_commit(&s_full[w]);
-    };
-    auto issue_pv = [&](int w, int st) {
-      const uint32_t sp = smem_u32(smem_p + w * kPBytes);
-      const uint32_t sv = smem_u32(smem_v + st * kTileBytes);
-#pragma unroll
-      for (int kb = 0; kb < kTileKV / 64; ++kb) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // A: k-block kb of P is a [128 x 64] K-major tile; B: box kb of V, 16 key rows per step
-          const uint64_t da = make_umma_smem_desc_sw128(sp + kb * kTileBytes + k * kUmmaKBytes, 0, 1024);
-          const uint64_t db = make_umma_smem_desc_sw128(sv + kb * (kTileBytes / 2) + k * 16 * 128,
-                                                        64 * 64 * 2, 1024);
-          umma_f16_ss(tmem_base + 2 * kTileKV + w * kHeadDim, da, db, idesc_o,
-                      (kb | k) != 0 ? 1u : 0u);
+  if (warp_idx >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp_idx == 8) {
+      // ================================ TMA producer ================================
+      if (elect_one()) {
+        uint32_t g = 0;                    // K/V ring position, runs across items
+        Item it;
+        for (int round = 0; get_item(p, round, it); ++round) {
+          const int row_base = it.b * p.T;
+          if (round > 0) mbar_wait(q_empty, (round - 1) & 1);
+          const int n_q = it.n_kv[1] > 0 ? 2 : 1;
+          mbar_expect_tx(q_full, n_q * kTileBytes);
+          for (int w = 0; w < n_q; ++w)
+            tma_load_2d(&tmap_q, q_full, smem_q + w * kTileBytes, it.h * kHeadDim,
+                        row_base + it.q0 + w * kTileQ);
+          for (int j = 0; j < it.n_max; ++j, ++g) {
+            const int st = g % kStagesKV;
+            const uint32_t ph = (g / kStagesKV) & 1;
+            mbar_wait(&k_empty[st], ph ^ 1);
+            mbar_expect_tx(&k_full[st], kTileBytes);
+            tma_load_2d(&tmap_k, &k_full[st], smem_k + st * kTileBytes, it.h * kHeadDim,
+                        row_base + j * kTileKV);
+            mbar_wait(&v_empty[st], ph ^ 1);
+            mbar_expect_tx(&v_full[st], kTileBytes);
+            // one [128 keys x 64 d] box: rows of 128 B, i.e. two stacked [64 x 64] boxes -- exactly
+            // the MN-major B operand of P.V (one 8 KiB box per 64-key k-block)
+            tma_load_2d(&tmap_v, &v_full[st], smem_v + st * kTileBytes, it.h * kHeadDim,
+                        row_base + j * kTileKV);
+          }
         }
       }
-      umma_commit(&o_full[w]);
-    };
+    } else if (warp_idx == 9) {
+      // ================================ MMA issuer ================================
+      // S = Q K^T : A = Q  [128 x 64]  K-major,  B = K [128 keys x 64] K-major   (N = 128)
+      // O+= P V   : A = P  [128 x 128] K-major (2 k-blocks), B = V [128 keys x 64] MN-major (N = 64)
+      const uint32_t idesc_s = make_idesc_bf16_f32(kTileQ, kTileKV, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16_f32(kTileQ, kHeadDim, 0, 1);
+      constexpr uint32_t kUmmaKBytes = 16 * 2;          // K = 16 bf16 along a 128-byte swizzled row
+      auto issue_s = [&](int w, int st) {
+        const uint32_t sa = smem_u32(smem_q + w * kTileBytes);
+        const uint32_t sb = smem_u32(smem_k + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          const uint64_t da = make_umma_smem_desc_sw128(sa + k * kUmmaKBytes, 0, 1024);
+          const uint64_t db = make_umma_smem_desc_sw128(sb + k * kUmmaKBytes, 0, 1024);
+          umma_f16_ss(tmem_base + w * kTileKV, da, db, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[w]);
+      };
+      auto issue_pv = [&](int w, int st, bool accumulate) {
+        const uint32_t sp = smem_u32(smem_p + w * kPBytes);
+        const uint32_t sv = smem_u32(smem_v + st * kTileBytes);
+#pragma unroll
+        for (int kb = 0; kb < kTileKV / 64; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // A: k-block kb of P is a [128 x 64] K-major tile; B: box kb of V, 16 key rows per step
+            const uint64_t da =
+                make_umma_smem_desc_sw128(sp + kb * kTileBytes + k * kUmmaKBytes, 0, 1024);
+            const uint64_t db = make_umma_smem_desc_sw128(
+                sv + kb * (kTileBytes / 2) + k * 16 * 128, 64 * 64 * 2, 1024);
+            umma_f16_ss(tmem_base + 2 * kTileKV + w * kHeadDim, da, db, idesc_o,
+                        (accumulate || (kb | k) != 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&o_full[w]);
+      };
 
-    mbar_wait(q_full, 0);
-    if (n_max > 0) {
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        for (int w = 0; w < 2; ++w)
-          if (n_kv[w] > 0) issue_s(w, 0);
-        umma_commit(&k_empty[0]);
-      }
-      __syncwarp();
-    }
-    for (int j = 0; j < n_max; ++j) {
-      const int st = j % kStagesKV, st1 = (j + 1) % kStagesKV;
-      const uint32_t ph = (j / kStagesKV) & 1, ph1 = ((j + 1) / kStagesKV) & 1;
-      mbar_wait(&v_full[st], ph);
-      if (j + 1 < n_max) mbar_wait(&k_full[st1], ph1);
-      for (int w = 0; w < 2; ++w) {
-        if (j >= n_kv[w]) continue;
-        mbar_wait(&p_ready[w], j & 1);          // P_w(j) in smem, S_w / O_w' free again
-        tc_fence_after();
-        if (elect_one()) {
-          issue_pv(w, st);
-          if (j + 1 < n_kv[w]) issue_s(w, st1);
+      uint32_t g = 0;
+      uint32_t cnt_p[2] = {0u, 0u};
+      Item it;
+      for (int round = 0; get_item(p, round, it); ++round) {
+        mbar_wait(q_full, round & 1);
+        {
+          const int st = g % kStagesKV;
+          mbar_wait(&k_full[st], (g / kStagesKV) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int w = 0; w < 2; ++w)
+              if (it.n_kv[w] > 0) issue_s(w, st);
+            umma_commit(&k_empty[st]);
+            if (it.n_max == 1) umma_commit(q_empty);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        for (int j = 0; j < it.n_max; ++j) {
+          const uint32_t gj = g + j;
+          const int st = gj % kStagesKV, st1 = (gj + 1) % kStagesKV;
+          const uint32_t ph = (gj / kStagesKV) & 1, ph1 = ((gj + 1) / kStagesKV) & 1;
+          mbar_wait(&v_full[st], ph);
+          if (j + 1 < it.n_max) mbar_wait(&k_full[st1], ph1);
+          for (int w = 0; w < 2; ++w) {
+            if (j >= it.n_kv[w]) continue;
+            mbar_wait(&p_ready[w], cnt_p[w] & 1);     // P_w(j) in smem, S_w free, O_w consistent
+            ++cnt_p[w];
+            tc_fence_after();
+            if (elect_one()) {
+              issue_pv(w, st, j > 0);
+              if (j + 1 < it.n_kv[w]) issue_s(w, st1);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit(&v_empty[st]);              // V(j) consumed once both P.V are complete
+            if (j + 1 < it.n_max) {
+              umma_commit(&k_empty[st1]);
+              if (j + 2 == it.n_max) umma_commit(q_empty);   // last S of the item has been issued
+            }
+          }
+          __syncwarp();
+        }
+        g += it.n_max;
       }
-      if (elect_one()) {
-        umma_commit(&v_empty[st]);              // V(j) consumed once both P.V are complete
-        if (j + 1 < n_max) umma_commit(&k_empty[st1]);
-      }
-      __syncwarp();
     }
   } else {
     // ================================ softmax warp-groups ================================
-    const int wg = (warp_idx - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int wg = warp_idx >> 2;
     const int quad = warp_idx & 3;
     const int row = quad * 32 + lane;                       // row in the 128-row tile = TMEM lane
-    const int n_mine = n_kv[wg];
     const uint32_t t_s = tmem_base + wg * kTileKV + (static_cast<uint32_t>(quad * 32) << 16);
-    const uint32_t t_o = tmem_base + 2 * kTileKV + wg * kHeadDim + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t t_o =
+        tmem_base + 2 * kTileKV + wg * kHeadDim + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* my_p = smem_p + wg * kPBytes;
     const int swz = row & 7;
-    float o[kHeadDim];
-#pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) o[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-
-    auto add_o_tile = [&]() {
-#pragma unroll
-      for (int c = 0; c < kHeadDim / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_o + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
-      }
-    };
-
-    for (int j = 0; j < n_mine; ++j) {
-      mbar_wait(&s_full[wg], j & 1);
-      tc_fence_after();
-      const bool diag = p.causal && (j == n_mine - 1);     // keys j*128 + c vs query q0+128wg+row
-      // ---- pass A: row max of the raw scores
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kTileKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          if (!diag || c * 32 + i <= row) mx = fmaxf(mx, s);
+    uint32_t cnt_s = 0, cnt_o = 0;
+    bool store_pending = false;                             // my_p is being read by a TMA store
+    Item it;
+    for (int round = 0; get_item(p, round, it); ++round) {
+      const int n_mine = it.n_kv[wg];
+      if (n_mine == 0) continue;
+      float m_run = 0.f, l_run = 0.f;
+      for (int j = 0; j < n_mine; ++j) {
+        mbar_wait(&s_full[wg], cnt_s & 1);
+        ++cnt_s;
+        if (j > 0) {
+          // PV(j-1) was issued before S(j): the tensor pipe completes in order, so this returns at
+          // once -- it only keeps the phase bookkeeping of o_full in step
+          mbar_wait(&o_full[wg], cnt_o & 1);
+          ++cnt_o;
         }
-      }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      // ---- fold the previous tile's P.V into the running output, then rescale to the new max
-      if (j > 0) {
-        mbar_wait(&o_full[wg], (j - 1) & 1);
         tc_fence_after();
-        add_o_tile();
-      }
-      const float alpha = ex2(m_run - m_new);               // 0 on the first tile (m_run = -inf)
+        uint32_t r[kTileKV];
 #pragma unroll
-      for (int d = 0; d < kHeadDim; ++d) o[d] *= alpha;
-      l_run *= alpha;
-      // ---- pass B: P = exp2(S * c - m), row sum, bf16 P into the K-major swizzled A tile
-      float lsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < kTileKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
+        for (int c = 0; c < kTileKV / 32; ++c) tmem_ld_x32_at(t_s + c * 32, r + c * 32);
         tmem_ld_wait();
-        uint32_t pk[16];
+        if (p.causal && j == n_mine - 1) {                  // keys j*128 + c vs query q0+128wg+row
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_new));
-          float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_new));
-          if (diag) {
-            if (c * 32 + i > row) p0 = 0.f;
-            if (c * 32 + i + 1 > row) p1 = 0.f;
+          for (int i = 0; i < kTileKV; ++i)
+            if (i > row) r[i] = 0xff800000u;                // -inf
+        }
+        float mx0 = __uint_as_float(r[0]), mx1 = __uint_as_float(r[1]);
+#pragma unroll
+        for (int i = 2; i < kTileKV; i += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          if (i + 3 < kTileKV) mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+        const float sm = fmaxf(mx0, mx1) * p.scale_log2;
+        if (j == 0) {
+          m_run = sm;
+        } else if (__any_sync(0xffffffffu, sm > m_run + kRescaleThreshold)) {
+          // rare: advance the running max and rescale O (in TMEM) and l
+          const float m_new = fmaxf(m_run, sm);
+          const float alpha = ex2(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < kHeadDim / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32_at(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, o);
           }
-          lsum += p0 + p1;
-          pk[i / 2] = pack_bf16x2(p0, p1);
+          tmem_st_wait();
         }
-        // columns [32c, 32c+32) = k-block c/2, 16-byte chunks (c%2)*4 .. +3 of this row
-        uint8_t* dst = my_p + (c >> 1) * kTileBytes + row * 128;
+        // the O tile of the previous item may still be leaving through my_p
+        if (store_pending) {
+          if (quad == 0 && lane == 0) tma_store_wait_read<0>();
+          wg_bar_sync(wg);
+          store_pending = false;
+        }
+        // ---- P = exp2(S * c - m), row sum, bf16 P into the K-major swizzled A tile
+        float ls0 = 0.f, ls1 = 0.f;
+        const float neg_m = -m_run;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c & 1) * 4 + q4;
-          *reinterpret_cast<uint4*>(dst + ((chunk ^ swz) << 4)) =
-              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        for (int c = 0; c < kTileKV / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[c * 32 + i]), p.scale_log2, neg_m));
+            const float p1 = ex2(fmaf(__uint_as_float(r[c * 32 + i + 1]), p.scale_log2, neg_m));
+            ls0 += p0;
+            ls1 += p1;
+            pk[i / 2] = pack_bf16x2(p0, p1);
+          }
+          // columns [32c, 32c+32) = k-block c/2, 16-byte chunks (c%2)*4 .. +3 of this row
+          uint8_t* dst = my_p + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (c & 1) * 4 + q4;
+            *reinterpret_cast<uint4*>(dst + ((chunk ^ swz) << 4)) =
+                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
         }
+        l_run += ls0 + ls1;
+        // S_w is drained, O_w is consistent, P_w is written: hand them to the MMA warp
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[wg]);
       }
-      l_run += lsum;
-      m_run = m_new;
-      // S_w and O_w' are drained, P_w is written: hand all three to the MMA warp
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[wg]);
-    }
 
-    if (n_mine > 0) {
-      mbar_wait(&o_full[wg], (n_mine - 1) & 1);
+      // ---- end of item: O / l -> bf16 -> swizzled staging (my_p: the last P.V has completed) -> TMA
+      mbar_wait(&o_full[wg], cnt_o & 1);
+      ++cnt_o;
       tc_fence_after();
-      add_o_tile();
-      const float inv_l = 1.f / l_run;
-      // ---- O tile -> swizzled staging (the P buffer is free: the last P.V has completed) -> TMA
-      uint8_t* dst = my_p + row * 128;
+      {
+        uint32_t o[kHeadDim];
 #pragma unroll
-      for (int q8 = 0; q8 < kHeadDim / 8; ++q8) {
-        uint4 v;
-        v.x = pack_bf16x2(o[8 * q8] * inv_l, o[8 * q8 + 1] * inv_l);
-        v.y = pack_bf16x2(o[8 * q8 + 2] * inv_l, o[8 * q8 + 3] * inv_l);
-        v.z = pack_bf16x2(o[8 * q8 + 4] * inv_l, o[8 * q8 + 5] * inv_l);
-        v.w = pack_bf16x2(o[8 * q8 + 6] * inv_l, o[8 * q8 + 7] * inv_l);
-        *reinterpret_cast<uint4*>(dst + ((q8 ^ swz) << 4)) = v;
+        for (int c = 0; c < kHeadDim / 32; ++c) tmem_ld_x32_at(t_o + c * 32, o + c * 32);
+        tmem_ld_wait();
+        const float inv_l = 1.f / l_run;
+        uint8_t* dst = my_p + row * 128;
+#pragma unroll
+        for (int q8 = 0; q8 < kHeadDim / 8; ++q8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * q8]) * inv_l, __uint_as_float(o[8 * q8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[8 * q8 + 2]) * inv_l, __uint_as_float(o[8 * q8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[8 * q8 + 4]) * inv_l, __uint_as_float(o[8 * q8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[8 * q8 + 6]) * inv_l, __uint_as_float(o[8 * q8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + ((q8 ^ swz) << 4)) = v;
+        }
       }
-      const int t = q0 + wg * kTileQ + row;
-      if (p.lse != nullptr && t < p.T)
-        p.lse[(static_cast<size_t>(b) * p.H + h) * p.T + t] =
+      const int t = it.q0 + wg * kTileQ + row;
+      if (p.lse != nullptr)
+        p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.T + t] =
             (m_run + lg2(l_run)) * 0.6931471805599453f;
+      tc_fence_before();                  // O_w has been read: the next item's first P.V may overwrite
       fence_proxy_async_smem();
       wg_bar_sync(wg);
-      if (quad == 2 && lane == 0) {       // warps 2 and 6 are the first warps of their groups
-        tma_store_2d(&tmap_o, my_p, p.o_col0 + h * kHeadDim, row_base + q0 + wg * kTileQ);
+      if (quad == 0 && lane == 0) {
+        tma_store_2d(&tmap_o, my_p, it.h * kHeadDim, it.b * p.T + it.q0 + wg * kTileQ);
         tma_store_commit();
-        tma_store_wait<0>();
       }
+      store_pending = true;
     }
+    if (quad == 0 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) {
+  if (warp_idx == 9) {
     tc_fence_after();
     tmem_dealloc<kTmemColsAttn>(tmem_base);
   }
@@ -380,23 +435,27 @@ int launch_attn_fwd(const AttnFwdLaunch& a, cudaStream_t stream, const char** er
     snprintf(msg, sizeof(msg), "attn_fwd: cuTensorMapEncodeTiled failed");
     return -2;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) {
       snprintf(msg, sizeof(msg), "attn_fwd: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
     }
-    attr_set = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
   }
   AttnParams p;
   p.B = a.B; p.T = a.T; p.H = a.H;
   p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  p.q_col0 = 0; p.k_col0 = 0; p.v_col0 = 0; p.o_col0 = 0;   // bases already point at head 0
+  p.n_qp = (a.T + 2 * kTileQ - 1) / (2 * kTileQ);
+  p.n_items = a.B * a.H * p.n_qp;
   p.lse = a.lse;
-  dim3 grid((a.T + 2 * kTileQ - 1) / (2 * kTileQ), a.H, a.B);
+  const int grid = p.n_items < num_sms ? p.n_items : num_sms;
   attn_fwd_sm100_kernel<<<grid, kAttnThreads, AttnSmem::kTotal, stream>>>(tq, tk, tv, to, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -199,24 +199,30 @@ struct AttnFwdLaunch {
 };
 int launch_attn_fwd(const AttnFwdLaunch& a, cudaStream_t stream, const char** err);
 
-// Flash-attention backward (same token-matrix contract).  lse: forward's [B, H, T]; delta:
-// rowsum(dO * O) as fp32 [B, H, T]; dq_acc: zero-initialised fp32 [B*T, H*D] accumulator (query
-// gradients of different key tiles are added with red.global); dk / dv: bf16 token matrices.
+// Flash-attention backward (same token-matrix contract), two kernels launched back to back:
+//   1. attn_bwd_dq_sm100.cu : delta = rowsum(dO * O) -> `delta` (fp32 [B, H, T] scratch) and dQ
+//   2. attn_bwd_sm100.cu    : dK, dV (reads lse and delta)
+// lse: forward's [B, H, T]; o: forward output; dq / dk / dv: bf16 token matrices (typically the
+// three column windows of one packed dqkv gradient).  No atomics, no fp32 accumulator.
 struct AttnBwdLaunch {
   const void* q;
   const void* k;
   const void* v;
+  const void* o;
   const void* d_o;
   const float* lse;
-  const float* delta;
-  float* dq_acc;
+  float* delta;
+  void* dq;
   void* dk;
   void* dv;
   int B, T, H, D;
-  int ld_q, ld_k, ld_v, ld_do, ld_dk, ld_dv;
+  int ld_q, ld_k, ld_v, ld_o, ld_do, ld_dq, ld_dk, ld_dv;
   int causal;
   float scale;
 };
+int launch_attn_bwd_dq(const AttnBwdLaunch& a, cudaStream_t stream, const char** err);
+int launch_attn_bwd_dkv(const AttnBwdLaunch& a, cudaStream_t stream, const char** err);
+// both, in order
 int launch_attn_bwd(const AttnBwdLaunch& a, cudaStream_t stream, const char** err);
 
 // ------------------------------------------------------------------ native symmetric memory

@@ -85,8 +85,9 @@ def native_attention_forward(qkv: torch.Tensor, n_head: int, causal: bool = True
 
 class _NativeAttnFn(torch.autograd.Function):
     """Forward and backward on the package's tcgen05 attention kernels.  q, k, v are read in place
-    from the packed projection; dk and dv are written by TMA straight into their column windows of
-    the packed gradient; dq is accumulated in fp32 across key tiles and cast into its window."""
+    from the packed projection; dq, dk and dv are written by TMA straight into their column
+    windows of the packed gradient (dQ and dK/dV each have their own output-stationary kernel, so
+    nothing is accumulated through global memory)."""
 
     @staticmethod
     def forward(ctx, qkv, n_head: int, causal: bool, scale: float):
@@ -104,14 +105,13 @@ class _NativeAttnFn(torch.autograd.Function):
         dh = D3 // 3 // H
         dout = dout.contiguous()
         do4, o4 = dout.view(B, T, H, dh), out.view(B, T, H, dh)
-        delta = (do4.float() * o4.float()).sum(-1).permute(0, 2, 1).contiguous()      # [B, H, T]
         qkv5 = qkv.view(B, T, 3, H, dh)
         dqkv = torch.empty_like(qkv)
         dqkv5 = dqkv.view(B, T, 3, H, dh)
-        dq_acc = torch.empty(B, T, H, dh, dtype=torch.float32, device=qkv.device)
-        C.attn_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], do4, lse, delta, dq_acc,
-                   dqkv5[:, :, 1], dqkv5[:, :, 2], bool(causal), float(scale))
-        dqkv5[:, :, 0].copy_(dq_acc)
+        delta = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)   # scratch
+        # two launches: (dQ + delta) then (dK, dV); all three land in their windows of dqkv
+        C.attn_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], o4, do4, lse, delta,
+                   dqkv5[:, :, 0], dqkv5[:, :, 1], dqkv5[:, :, 2], bool(causal), float(scale))
         return dqkv, None, None, None
 
 
