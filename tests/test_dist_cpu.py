@@ -402,7 +402,21 @@ def _w_tp_transformer(rank, world):
     for pb, sb in zip(par.blocks, serial.blocks):
         pb.init_from_full(sb)
     x = torch.randn(4, 5, 16)
-    assert torch.allclose(par(x), serial(x), atol=1e-4)
+    out_p, out_s = par(x), serial(x)
+    assert torch.allclose(out_p, out_s, atol=1e-4)
+    # gradient parity with the serial stack (replicated loss on the gathered output)
+    from torchdistpackage_b200.parallel.tensor_parallel.transformer import allreduce_sequence_parallel_grads
+    out_p.pow(2).sum().backward()
+    out_s.pow(2).sum().backward()
+    allreduce_sequence_parallel_grads(par)
+    tp = tdp.tpc.get_tp_rank() if tdp.tpc.is_mode_inited("tensor") else rank
+    for pb, sb in zip(par.blocks, serial.blocks):
+        assert torch.allclose(pb.ln_1.weight.grad, sb.ln_1.weight.grad, rtol=1e-3, atol=1e-4)
+        assert torch.allclose(pb.ln_2.bias.grad, sb.ln_2.bias.grad, rtol=1e-3, atol=1e-4)
+        g_full = sb.mlp.fc2.weight.grad            # row-parallel: split along the input features
+        g_mine = pb.mlp.fc2.linear.weight.grad
+        n = g_mine.shape[0]
+        assert torch.allclose(g_mine, g_full[rank * n:(rank + 1) * n], rtol=1e-3, atol=1e-4)
 
 
 def test_tp_sp_transformer_forward():
@@ -436,6 +450,31 @@ def _w_clip(rank, world):
 
 def test_clip_grad_norm_model_parallel():
     run_distributed(_w_clip, 4)
+
+
+def _w_clip_zero_tp(rank, world):
+    """ZeRO (over the data group) x tensor parallel: TP-replicated parameters must be counted
+    once in the global norm, TP shards on every TP rank."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import clip_grad_norm_
+    tdp.tpc.setup_process_groups([("data", 2), ("tensor", 2)])
+    tp, dp = tdp.tpc.get_tp_rank(), tdp.tpc.get_group_rank("data")
+    torch.manual_seed(0)
+    w_full, b_full = torch.randn(6, 40), torch.randn(72)      # same gradient on both DP replicas
+    w = nn.Parameter(torch.zeros(3, 40)); w.tensor_model_parallel = True
+    b = nn.Parameter(torch.zeros(72))
+    zopt = tdp.Bf16ZeroOptimizer(torch.optim.SGD([w, b], lr=0.1), dp_group=tdp.tpc.get_group("data"),
+                                 bucket_size=64)
+    with torch.no_grad():
+        w.grad.copy_(w_full[tp * 3:(tp + 1) * 3])
+        b.grad.copy_(b_full)
+    norm = clip_grad_norm_([], max_norm=1.0, zero_optimizer=zopt)
+    expect = (w_full.pow(2).sum() + b_full.pow(2).sum()).sqrt()
+    assert torch.allclose(norm, expect, rtol=1e-5), (norm, expect)
+
+
+def test_clip_grad_norm_zero_with_tensor_parallel():
+    run_distributed(_w_clip_zero_tp, 4)
 
 
 # ------------------------------------------------------------------ MoE layer (expert parallel)

@@ -112,8 +112,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
   uint64_t* v_full = k_empty + kStages;
   uint64_t* v_empty = v_full + kStages;
   uint64_t* s_full = v_empty + kStages;          // 2: S'_w and dP'_w ready
-  uint64_t* p_ready = s_full + 2;                // 2: dS_w written, S'_w / dP'_w consumed
-  uint64_t* dq_full = p_ready + 2;               // 2: all dQ_w MMAs of the item complete
+  uint64_t* s_free = s_full + 2;                 // 2: S'_w / dP'_w are in registers (TMEM reusable)
+  uint64_t* p_ready = s_free + 2;                // 2: dS_w written
+  uint64_t* dq_full = p_ready + 2;               // 2: dQ_w += dS_w K' (one completion per sub-tile)
   uint64_t* stage_free = dq_full + 2;            // 2: the dQ_w store has read its staging tile
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stage_free + 2);
 
@@ -137,6 +138,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
     }
     for (int w = 0; w < 2; ++w) {
       mbar_init(&s_full[w], 1);
+      mbar_init(&s_free[w], 4);
       mbar_init(&p_ready[w], 4);
       mbar_init(&dq_full[w], 1);
       mbar_init(&stage_free[w], 1);
@@ -210,59 +212,78 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
         umma_commit(&s_full[w]);
       };
 
-      uint32_t g = 0;
-      uint32_t cnt_p[2] = {0u, 0u};
-      Item it;
-      for (int round = 0; get_item(p, round, it); ++round) {
-        mbar_wait(q_full, round & 1);
-        {
-          const int st = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
-          mbar_wait(&k_full[st], ph);
-          mbar_wait(&v_full[st], ph);
+      // Event-driven issue loop (one thread), same scheme as the forward kernel:
+      //   s_free[w]  (S'_w, dP'_w(j) are in registers)  -> issue S'_w, dP'_w(j+1)
+      //   p_ready[w] (dS_w(j) is in smem)                -> issue dQ_w += dS_w(j) K'(j)
+      if (elect_one()) {
+        uint32_t g = 0;
+        uint32_t a_cnt[2] = {0u, 0u}, b_cnt[2] = {0u, 0u};
+        Item it;
+        for (int round = 0; get_item(p, round, it); ++round) {
+          int a_loc[2] = {0, 0}, b_loc[2] = {0, 0};
+          int s_iss[2] = {0, 0};
+          int rk = 0, rv = 0;
+          bool q_released = false;
+          auto release = [&]() {
+            // K'(jj): read by S'(jj) and by dQ(jj) of both groups; V'(jj): by dP'(jj)
+            while (rk < it.n_max && (b_loc[0] > rk || rk >= it.n_sub[0]) &&
+                   (b_loc[1] > rk || rk >= it.n_sub[1])) {
+              umma_commit(&k_empty[(g + rk) % kStages]);
+              ++rk;
+            }
+            while (rv < it.n_max && (s_iss[0] > rv || rv >= it.n_sub[0]) &&
+                   (s_iss[1] > rv || rv >= it.n_sub[1])) {
+              umma_commit(&v_empty[(g + rv) % kStages]);
+              ++rv;
+            }
+            if (!q_released && s_iss[0] >= it.n_sub[0] && s_iss[1] >= it.n_sub[1]) {
+              umma_commit(q_empty);
+              q_released = true;
+            }
+          };
+          mbar_wait(q_full, round & 1);
+          mbar_wait(&k_full[g % kStages], (g / kStages) & 1);
+          mbar_wait(&v_full[g % kStages], (g / kStages) & 1);
           tc_fence_after();
-          if (elect_one()) {
-            for (int w = 0; w < 2; ++w)
-              if (it.n_sub[w] > 0) issue_sdp(w, st);
-            umma_commit(&v_empty[st]);
-            if (it.n_max == 1) umma_commit(q_empty);
-          }
-          __syncwarp();
-        }
-        for (int j = 0; j < it.n_max; ++j) {
-          const uint32_t gj = g + j;
-          const int st = gj % kStages, st1 = (gj + 1) % kStages;
-          const uint32_t ph1 = ((gj + 1) / kStages) & 1;
-          if (j + 1 < it.n_max) {
-            mbar_wait(&k_full[st1], ph1);
-            mbar_wait(&v_full[st1], ph1);
-          }
-          for (int w = 0; w < 2; ++w) {
-            if (j >= it.n_sub[w]) continue;
-            mbar_wait(&p_ready[w], cnt_p[w] & 1);
-            ++cnt_p[w];
-            tc_fence_after();
-            if (elect_one()) {
-              // dQ first, then the next S' / dP': in-order completion makes "S'(j+1) ready" imply
-              // "dQ(j) done reading dS_w", which is what lets the warp-group overwrite dS_w
-              mma_dq(kColDQ + w * kD, smem_u32(smem_ds + w * kQTile), smem_u32(smem_k + st * kKTile),
-                     j > 0);
-              if (j + 1 == it.n_sub[w]) umma_commit(&dq_full[w]);
-              if (j + 1 < it.n_sub[w]) issue_sdp(w, st1);
-            }
-            __syncwarp();
-          }
-          if (elect_one()) {
-            umma_commit(&k_empty[st]);
-            if (j + 1 < it.n_max) {
-              umma_commit(&v_empty[st1]);
-              if (j + 2 == it.n_max) umma_commit(q_empty);
+          for (int w = 0; w < 2; ++w)
+            if (it.n_sub[w] > 0) { issue_sdp(w, g % kStages); s_iss[w] = 1; }
+          release();
+          while (a_loc[0] < it.n_sub[0] || b_loc[0] < it.n_sub[0] || a_loc[1] < it.n_sub[1] ||
+                 b_loc[1] < it.n_sub[1]) {
+            for (int w = 0; w < 2; ++w) {
+              if (a_loc[w] < it.n_sub[w] && mbar_try_wait(&s_free[w], a_cnt[w] & 1)) {
+                const int j = a_loc[w];
+                const uint32_t gj = g + j + 1;
+                if (j + 1 >= it.n_sub[w]) {
+                  ++a_cnt[w];
+                  ++a_loc[w];
+                } else if (mbar_try_wait(&k_full[gj % kStages], (gj / kStages) & 1) &&
+                           mbar_try_wait(&v_full[gj % kStages], (gj / kStages) & 1)) {
+                  ++a_cnt[w];
+                  ++a_loc[w];
+                  tc_fence_after();
+                  issue_sdp(w, gj % kStages);
+                  s_iss[w] = j + 2;
+                  release();
+                }
+              }
+              if (b_loc[w] < it.n_sub[w] && mbar_try_wait(&p_ready[w], b_cnt[w] & 1)) {
+                ++b_cnt[w];
+                const int j = b_loc[w];
+                tc_fence_after();
+                // K'(j) is resident: S'_w(j) was computed from it and it is released below
+                mma_dq(kColDQ + w * kD, smem_u32(smem_ds + w * kQTile),
+                       smem_u32(smem_k + ((g + j) % kStages) * kKTile), j > 0);
+                umma_commit(&dq_full[w]);
+                b_loc[w] = j + 1;
+                release();
+              }
             }
           }
-          __syncwarp();
+          g += it.n_max;
         }
-        g += it.n_max;
       }
+      __syncwarp();
     }
   } else {
     // ================================ softmax warp-groups ================================
@@ -315,6 +336,10 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
         tmem_ld_x32_at(t_dp, rp);
         tmem_ld_x32_at(t_dp + 32, rp + 32);
         tmem_ld_wait();
+        // both slices are in registers: let the tensor core produce the next pair right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[wg]);
         // keys j*64 + c are visible to query t iff j*64 + c <= t (only the last sub-tiles cut)
         const int lim = p.causal ? (t - j * kSub) : kSub;     // columns c <= lim are kept
         uint32_t dd[kSub / 2];
@@ -327,12 +352,15 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
           dd[e / 2] = pack_bf16x2(p0 * (__uint_as_float(rp[e]) - dlt),
                                   p1 * (__uint_as_float(rp[e + 1]) - dlt));
         }
+        if (j > 0) {                       // dQ(j-1) has finished reading my dS tile
+          mbar_wait(&dq_full[wg], cnt_dq & 1);
+          ++cnt_dq;
+        }
         uint8_t* dst = my_ds + row * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<uint4*>(dst + ((c ^ swz) << 4)) =
               make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
-        tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[wg]);

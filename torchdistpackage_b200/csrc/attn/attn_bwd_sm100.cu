@@ -85,7 +85,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
   uint64_t* s_full = q_empty + kQStages;         // S_i and dP_i ready
   uint64_t* p_ready = s_full + 1;                // 2 (per P/dS buffer): written, S/dP consumed
   uint64_t* pds_free = p_ready + 2;              // 2: the MMAs reading buffer u have completed
-  uint64_t* dkv_full = pds_free + 2;             // all of dK / dV accumulated
+  uint64_t* sdp_free = pds_free + 2;             // S_i / dP_i are in registers (TMEM reusable)
+  uint64_t* dkv_full = sdp_free + 1;             // all of dK / dV accumulated
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(dkv_full + 1);
 
   const int warp_idx = threadIdx.x / 32;
@@ -111,6 +112,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
       mbar_init(&p_ready[u], 8);               // one elected lane per softmax warp (2 groups)
       mbar_init(&pds_free[u], 1);
     }
+    mbar_init(sdp_free, 8);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   } else if (warp_idx == 9) {
@@ -182,9 +184,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
       const int s = it % kQStages, u = it & 1;
       const uint32_t sq = smem_u32(smem_q + s * 2 * kTile), sdo = sq + kTile;
       const uint32_t sp = smem_u32(smem_pds + u * 2 * kPTile), sds = sp + kPTile;
-      mbar_wait(&p_ready[u], (it >> 1) & 1);                    // P_i, dS_i written; S / dP drained
-      tc_fence_after();
-      // next tile's S / dP first: the softmax group can start on it while dV / dK / dQ run
+      // S_i / dP_i have been read into registers: produce the next pair right away, so the
+      // softmax groups never wait for the tensor core (their registers are the second buffer)
+      mbar_wait(sdp_free, it & 1);
       if (it + 1 < n_iter) {
         const int s1 = (it + 1) % kQStages;
         mbar_wait(&q_full[s1], ((it + 1) / kQStages) & 1);
@@ -196,6 +198,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
         }
         __syncwarp();
       }
+      mbar_wait(&p_ready[u], (it >> 1) & 1);                    // P_i, dS_i written
+      tc_fence_after();
       if (elect_one()) {
         mma_tn(kColDV, sp, sdo, it > 0);                        // dV += P^T dO_i
         mma_tn(kColDK, sds, sq, it > 0);                        // dK += dS^T Q_i
@@ -230,6 +234,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
       tmem_ld_x32_at(tmem_base + kColDP + wg * 64 + lane_off, rp);
       tmem_ld_x32_at(tmem_base + kColDP + wg * 64 + 32 + lane_off, rp + 32);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);
       // causal diagonal tile (i == j): key wg*64 + e is visible to query `row` iff <= row
       const int lim = (p.causal && i == j) ? (row - wg * 64) : 64;
       uint32_t pp[32], dd[32];
@@ -255,7 +262,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {64,
         *reinterpret_cast<uint4*>(dsbuf + off + chunk) =
             make_uint4(dd[4 * c], dd[4 * c + 1], dd[4 * c + 2], dd[4 * c + 3]);
       }
-      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[u]);

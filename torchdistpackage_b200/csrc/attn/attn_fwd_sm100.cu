@@ -16,7 +16,8 @@
 //
 //   per KV tile j and warp-group w:
 //     S_w  = Q_w K_j^T           UMMA 128x128x64   -> TMEM cols [128w, 128w+128)
-//     WG w: one TMEM read of the whole 128-column row, row max; the running max m is only
+//     WG w: one TMEM read of the whole 128-column row (the TMEM region is released at once, so
+//           S_w(j+1) is computed while the group still works on tile j), row max; the running max m is only
 //           advanced (and O_w / l rescaled, in TMEM) when the new max exceeds it by > 2^8 --
 //           rare after the first tile, so the O correction is off the critical path
 //           P = exp2(S*c - m) -> bf16 -> swizzled smem (A operand)
@@ -121,7 +122,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
   uint64_t* v_full = k_empty + kStagesKV;
   uint64_t* v_empty = v_full + kStagesKV;
   uint64_t* s_full = v_empty + kStagesKV;        // 2: S_w ready for warp-group w
-  uint64_t* p_ready = s_full + 2;                // 2: P_w written (and S_w consumed, O_w consistent)
+  uint64_t* s_free = s_full + 2;                 // 2: S_w is in registers, TMEM region reusable
+  uint64_t* p_ready = s_free + 2;                // 2: P_w written (O_w consistent)
   uint64_t* o_full = p_ready + 2;                // 2: O_w += P_w V complete
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_full + 2);
 
@@ -143,7 +145,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
     }
     for (int w = 0; w < 2; ++w) {
       mbar_init(&s_full[w], 1);
-      mbar_init(&p_ready[w], 4);      // one elected lane per warp of the warp-group
+      mbar_init(&s_free[w], 4);       // one elected lane per warp of the warp-group
+      mbar_init(&p_ready[w], 4);
       mbar_init(&o_full[w], 1);
     }
     fence_barrier_init();
@@ -223,51 +226,81 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
         umma_commit(&o_full[w]);
       };
 
-      uint32_t g = 0;
-      uint32_t cnt_p[2] = {0u, 0u};
-      Item it;
-      for (int round = 0; get_item(p, round, it); ++round) {
-        mbar_wait(q_full, round & 1);
-        {
-          const int st = g % kStagesKV;
-          mbar_wait(&k_full[st], (g / kStagesKV) & 1);
+      // Event-driven issue loop (one thread): per warp-group two event streams,
+      //   s_free[w]  (S_w(j) has been read into registers)  -> issue S_w(j+1)
+      //   p_ready[w] (P_w(j) is in smem)                     -> issue O_w += P_w(j) V(j)
+      // served in arrival order by polling, so the two softmax groups drift half a period apart
+      // (true ping-pong) and S_w(j+1) is computed while group w still works on tile j.
+      if (elect_one()) {
+        uint32_t g = 0;
+        uint32_t a_cnt[2] = {0u, 0u}, b_cnt[2] = {0u, 0u};     // events consumed (phase parity)
+        Item it;
+        for (int round = 0; get_item(p, round, it); ++round) {
+          int a_loc[2] = {0, 0}, b_loc[2] = {0, 0};            // per item
+          int s_iss[2] = {0, 0};                               // S_w(0..s_iss-1) issued
+          int rk = 0, rv = 0;                                  // K / V tiles released so far
+          bool q_released = false;
+          auto release = [&]() {
+            // K(jj) is free once every group that needs it has had S(jj) issued, V(jj) once
+            // every group has had its P.V(jj) issued (commit = when those MMAs complete)
+            while (rk < it.n_max && (s_iss[0] > rk || rk >= it.n_kv[0]) &&
+                   (s_iss[1] > rk || rk >= it.n_kv[1])) {
+              umma_commit(&k_empty[(g + rk) % kStagesKV]);
+              ++rk;
+            }
+            while (rv < it.n_max && (b_loc[0] > rv || rv >= it.n_kv[0]) &&
+                   (b_loc[1] > rv || rv >= it.n_kv[1])) {
+              umma_commit(&v_empty[(g + rv) % kStagesKV]);
+              ++rv;
+            }
+            if (!q_released && s_iss[0] >= it.n_kv[0] && s_iss[1] >= it.n_kv[1]) {
+              umma_commit(q_empty);                            // last S of the item issued
+              q_released = true;
+            }
+          };
+          mbar_wait(q_full, round & 1);
+          mbar_wait(&k_full[g % kStagesKV], (g / kStagesKV) & 1);
           tc_fence_after();
-          if (elect_one()) {
-            for (int w = 0; w < 2; ++w)
-              if (it.n_kv[w] > 0) issue_s(w, st);
-            umma_commit(&k_empty[st]);
-            if (it.n_max == 1) umma_commit(q_empty);
-          }
-          __syncwarp();
-        }
-        for (int j = 0; j < it.n_max; ++j) {
-          const uint32_t gj = g + j;
-          const int st = gj % kStagesKV, st1 = (gj + 1) % kStagesKV;
-          const uint32_t ph = (gj / kStagesKV) & 1, ph1 = ((gj + 1) / kStagesKV) & 1;
-          mbar_wait(&v_full[st], ph);
-          if (j + 1 < it.n_max) mbar_wait(&k_full[st1], ph1);
-          for (int w = 0; w < 2; ++w) {
-            if (j >= it.n_kv[w]) continue;
-            mbar_wait(&p_ready[w], cnt_p[w] & 1);     // P_w(j) in smem, S_w free, O_w consistent
-            ++cnt_p[w];
-            tc_fence_after();
-            if (elect_one()) {
-              issue_pv(w, st, j > 0);
-              if (j + 1 < it.n_kv[w]) issue_s(w, st1);
+          for (int w = 0; w < 2; ++w)
+            if (it.n_kv[w] > 0) { issue_s(w, g % kStagesKV); s_iss[w] = 1; }
+          release();
+          while (a_loc[0] < it.n_kv[0] || b_loc[0] < it.n_kv[0] || a_loc[1] < it.n_kv[1] ||
+                 b_loc[1] < it.n_kv[1]) {
+            for (int w = 0; w < 2; ++w) {
+              // an event is only consumed when the K / V stage it needs has landed: a blocking
+              // wait here could starve the other group, whose progress frees ring stages
+              if (a_loc[w] < it.n_kv[w] && mbar_try_wait(&s_free[w], a_cnt[w] & 1)) {
+                const int j = a_loc[w];
+                const uint32_t gj = g + j + 1;
+                if (j + 1 >= it.n_kv[w]) {
+                  ++a_cnt[w];
+                  ++a_loc[w];
+                } else if (mbar_try_wait(&k_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
+                  ++a_cnt[w];
+                  ++a_loc[w];
+                  tc_fence_after();
+                  issue_s(w, gj % kStagesKV);
+                  s_iss[w] = j + 2;
+                  release();
+                }
+              }
+              if (b_loc[w] < it.n_kv[w] && mbar_try_wait(&p_ready[w], b_cnt[w] & 1)) {
+                const int j = b_loc[w];
+                const uint32_t gj = g + j;
+                if (mbar_try_wait(&v_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
+                  ++b_cnt[w];
+                  tc_fence_after();
+                  issue_pv(w, gj % kStagesKV, j > 0);
+                  b_loc[w] = j + 1;
+                  release();
+                }
+              }
             }
-            __syncwarp();
           }
-          if (elect_one()) {
-            umma_commit(&v_empty[st]);              // V(j) consumed once both P.V are complete
-            if (j + 1 < it.n_max) {
-              umma_commit(&k_empty[st1]);
-              if (j + 2 == it.n_max) umma_commit(q_empty);   // last S of the item has been issued
-            }
-          }
-          __syncwarp();
+          g += it.n_max;
         }
-        g += it.n_max;
       }
+      __syncwarp();
     }
   } else {
     // ================================ softmax warp-groups ================================
@@ -290,17 +323,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
       for (int j = 0; j < n_mine; ++j) {
         mbar_wait(&s_full[wg], cnt_s & 1);
         ++cnt_s;
-        if (j > 0) {
-          // PV(j-1) was issued before S(j): the tensor pipe completes in order, so this returns at
-          // once -- it only keeps the phase bookkeeping of o_full in step
-          mbar_wait(&o_full[wg], cnt_o & 1);
-          ++cnt_o;
-        }
         tc_fence_after();
         uint32_t r[kTileKV];
 #pragma unroll
         for (int c = 0; c < kTileKV / 32; ++c) tmem_ld_x32_at(t_s + c * 32, r + c * 32);
         tmem_ld_wait();
+        // S_w lives in registers now: release the TMEM region so that S_w(j+1) is computed while
+        // this group is still busy with tile j (the registers are the second buffer)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[wg]);
+        bool pv_done = (j == 0);            // has P.V(j-1) been waited for (P tile free, O final)?
         if (p.causal && j == n_mine - 1) {                  // keys j*128 + c vs query q0+128wg+row
 #pragma unroll
           for (int i = 0; i < kTileKV; ++i)
@@ -317,6 +350,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
           m_run = sm;
         } else if (__any_sync(0xffffffffu, sm > m_run + kRescaleThreshold)) {
           // rare: advance the running max and rescale O (in TMEM) and l
+          mbar_wait(&o_full[wg], cnt_o & 1);      // O_w must hold all of P.V(0..j-1)
+          ++cnt_o;
+          pv_done = true;
+          tc_fence_after();
           const float m_new = fmaxf(m_run, sm);
           const float alpha = ex2(m_run - m_new);
           m_run = m_new;
@@ -332,37 +369,44 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
           }
           tmem_st_wait();
         }
-        // the O tile of the previous item may still be leaving through my_p
+        // ---- P = exp2(S * c - m) (in registers, as bf16 pairs), row sum
+        float ls0 = 0.f, ls1 = 0.f;
+        const float neg_m = -m_run;
+        uint32_t pk[kTileKV / 2];
+#pragma unroll
+        for (int i = 0; i < kTileKV; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m));
+          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, neg_m));
+          ls0 += p0;
+          ls1 += p1;
+          pk[i / 2] = pack_bf16x2(p0, p1);
+        }
+        l_run += ls0 + ls1;
+        // ---- the P tile is free once P.V(j-1) has completed (issued a whole softmax ago)
+        if (!pv_done) {
+          mbar_wait(&o_full[wg], cnt_o & 1);
+          ++cnt_o;
+        }
+        // ... and once the O tile of the previous item has left through it
         if (store_pending) {
           if (quad == 0 && lane == 0) tma_store_wait_read<0>();
           wg_bar_sync(wg);
           store_pending = false;
         }
-        // ---- P = exp2(S * c - m), row sum, bf16 P into the K-major swizzled A tile
-        float ls0 = 0.f, ls1 = 0.f;
-        const float neg_m = -m_run;
+        // bf16 P into the K-major swizzled A tile: columns [32c, 32c+32) = k-block c/2,
+        // 16-byte chunks (c%2)*4 .. +3 of this row
 #pragma unroll
         for (int c = 0; c < kTileKV / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[c * 32 + i]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(r[c * 32 + i + 1]), p.scale_log2, neg_m));
-            ls0 += p0;
-            ls1 += p1;
-            pk[i / 2] = pack_bf16x2(p0, p1);
-          }
-          // columns [32c, 32c+32) = k-block c/2, 16-byte chunks (c%2)*4 .. +3 of this row
           uint8_t* dst = my_p + (c >> 1) * kTileBytes + row * 128;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const int chunk = (c & 1) * 4 + q4;
             *reinterpret_cast<uint4*>(dst + ((chunk ^ swz) << 4)) =
-                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                make_uint4(pk[16 * c + 4 * q4], pk[16 * c + 4 * q4 + 1], pk[16 * c + 4 * q4 + 2],
+                           pk[16 * c + 4 * q4 + 3]);
           }
         }
-        l_run += ls0 + ls1;
-        // S_w is drained, O_w is consistent, P_w is written: hand them to the MMA warp
+        // O_w is consistent, P_w is written: hand them to the MMA warp
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();

@@ -150,6 +150,10 @@ void launch_ema_update_multi(void* const* ema_ptrs, const void* const* param_ptr
                              int n_tensors, float decay, cudaStream_t stream);
 
 // sum of squares of a flat buffer into *out (fp32, atomically accumulated; caller zeroes)
+void launch_sumsq_multi(const void* const* ptrs, const int64_t* numels, const int* dtypes,
+                        int n_tensors, float* out, cudaStream_t stream);
+void launch_scale_multi(void* const* ptrs, const int64_t* numels, const int* dtypes, int n_tensors,
+                        float scale, const float* scale_ptr, cudaStream_t stream);
 void launch_sumsq(const void* x, int dtype, size_t numel, float* out, cudaStream_t stream);
 void launch_scale_(void* x, int dtype, size_t numel, float scale, const float* scale_ptr,
                    cudaStream_t stream);

@@ -207,6 +207,68 @@ scale_kernel(void* x, size_t numel, float scale, const float* scale_ptr) {
     store1<kBf16>(x, i, load1<kBf16>(x, i) * scale);
 }
 
+// multi-tensor variants (blockIdx.y = tensor index): one launch for a whole gradient list
+// (clip_grad_norm_: reference parallel/pipeline_parallel/clip_grad_parallel.py:40-77 loops in Python)
+template <bool kBf16>
+__device__ __forceinline__ float sumsq_range(const void* x, size_t numel, size_t tid, size_t stride) {
+  float acc = 0.f;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const size_t n4 = aligned ? numel / 4 : 0;
+  for (size_t i = tid; i < n4; i += stride) {
+    float v[4];
+    load4<kBf16>(x, i, v);
+    acc += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  }
+  for (size_t i = n4 * 4 + tid; i < numel; i += stride) {
+    const float v = load1<kBf16>(x, i);
+    acc += v * v;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+sumsq_multi_kernel(const void* const* ptrs, const int64_t* numels, const int* dtypes, float* out) {
+  const int t = blockIdx.y;
+  const size_t n = static_cast<size_t>(numels[t]);
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  float acc = dtypes[t] == 0 ? sumsq_range<true>(ptrs[t], n, tid, stride)
+                             : sumsq_range<false>(ptrs[t], n, tid, stride);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(out, acc);
+}
+
+__global__ void __launch_bounds__(kThreads)
+scale_multi_kernel(void* const* ptrs, const int64_t* numels, const int* dtypes, float scale,
+                   const float* scale_ptr) {
+  if (scale_ptr) scale *= *scale_ptr;
+  const int t = blockIdx.y;
+  const size_t n = static_cast<size_t>(numels[t]);
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  void* x = ptrs[t];
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const size_t n4 = aligned ? n / 4 : 0;
+  if (dtypes[t] == 0) {
+    for (size_t i = tid; i < n4; i += stride) {
+      float v[4];
+      load4<true>(x, i, v);
+      v[0] *= scale; v[1] *= scale; v[2] *= scale; v[3] *= scale;
+      store4<true>(x, i, v);
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += stride) store1<true>(x, i, load1<true>(x, i) * scale);
+  } else {
+    for (size_t i = tid; i < n4; i += stride) {
+      float v[4];
+      load4<false>(x, i, v);
+      v[0] *= scale; v[1] *= scale; v[2] *= scale; v[3] *= scale;
+      store4<false>(x, i, v);
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += stride) store1<false>(x, i, load1<false>(x, i) * scale);
+  }
+}
+
 template <bool kDstBf16, bool kSrcBf16>
 __global__ void __launch_bounds__(kThreads)
 cast_copy_kernel(void* dst, const void* src, size_t numel, float scale) {
@@ -278,6 +340,20 @@ void launch_scale_(void* x, int dtype, size_t numel, float scale, const float* s
   const int grid = grid_for(numel / 4 + 1, 2);
   if (dtype == 0) scale_kernel<true><<<grid, kThreads, 0, stream>>>(x, numel, scale, scale_ptr);
   else scale_kernel<false><<<grid, kThreads, 0, stream>>>(x, numel, scale, scale_ptr);
+}
+
+void launch_sumsq_multi(const void* const* ptrs, const int64_t* numels, const int* dtypes,
+                        int n_tensors, float* out, cudaStream_t stream) {
+  if (n_tensors <= 0) return;
+  dim3 grid(32, n_tensors);
+  sumsq_multi_kernel<<<grid, kThreads, 0, stream>>>(ptrs, numels, dtypes, out);
+}
+
+void launch_scale_multi(void* const* ptrs, const int64_t* numels, const int* dtypes, int n_tensors,
+                        float scale, const float* scale_ptr, cudaStream_t stream) {
+  if (n_tensors <= 0) return;
+  dim3 grid(32, n_tensors);
+  scale_multi_kernel<<<grid, kThreads, 0, stream>>>(ptrs, numels, dtypes, scale, scale_ptr);
 }
 
 void launch_cast_copy(void* dst, int dst_dtype, const void* src, int src_dtype, size_t numel,

@@ -510,13 +510,46 @@ class Bf16ZeroOptimizer:
         self._all_gather_params()
 
     # grad-norm support (used by clip_grad_norm_): squared L2 norm of this rank's shard
-    def local_grad_sq_norm(self) -> torch.Tensor:
+    def _shard_mask(self, include) -> List[torch.Tensor]:
+        """Per param group, a {0,1} fp32 vector over this rank's master shard: 1 where the element
+        belongs to a parameter for which ``include(p)`` is true (cached per predicate)."""
+        key = getattr(include, "__name__", repr(include))
+        cache = self.__dict__.setdefault("_mask_cache", {})
+        if key in cache:
+            return cache[key]
+        masks = []
+        for gi, params in enumerate(self.model_param_groups):
+            gb = [b for b in self.buckets if b.group_idx == gi]
+            mask = torch.zeros(sum(b.slice for b in gb), dtype=torch.float32, device=self.device)
+            base = self.flat_param[gi].data_ptr()
+            esize = self.flat_param[gi].element_size()
+            for p in params:
+                if not include(p):
+                    continue
+                lo = (p.data.data_ptr() - base) // esize
+                hi = lo + p.numel()
+                o = 0
+                for b in gb:
+                    s0 = b.start + self.rank * b.slice          # my slice of this bucket (flat coords)
+                    a, z = max(lo, s0), min(hi, s0 + b.slice)
+                    if a < z:
+                        mask[o + a - s0:o + z - s0] = 1.0
+                    o += b.slice
+            masks.append(mask)
+        cache[key] = masks
+        return masks
+
+    def local_grad_sq_norm(self, include=None) -> torch.Tensor:
+        """Squared L2 norm of this rank's gradient shard; ``include(p) -> bool`` restricts it to
+        the elements of selected parameters (clip_grad_norm_ under tensor parallelism)."""
         self.finish_bucket()
         if self.on_cuda:
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         total = torch.zeros((), dtype=torch.float32, device=self.device)
-        for mg in self.master_grad:
-            total = total + mg.float().pow(2).sum()
+        masks = self._shard_mask(include) if include is not None else None
+        for gi, mg in enumerate(self.master_grad):
+            sq = mg.float().pow(2)
+            total = total + (sq.sum() if masks is None else (sq * masks[gi]).sum())
         return total
 
     def scale_master_grads(self, coef) -> None:

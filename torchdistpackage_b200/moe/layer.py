@@ -104,9 +104,13 @@ class _A2AContext:
                 self.sym = sg
 
     def buffer(self, name: str, rows: int):
+        """Two ping-pong halves of ``rows`` slots each (zero-initialised) + the use counter."""
         key = (name, rows)
         if key not in self.bufs:
-            self.bufs[key] = self.sym.alloc(rows * self.hidden * 2)
+            buf = self.sym.alloc(2 * rows * self.hidden * 2)
+            buf.view(0, (2 * rows, self.hidden), torch.bfloat16).zero_()
+            buf.barrier(0)                  # nobody scatters into a half that is not cleared yet
+            self.bufs[key] = [buf, 0]
         return self.bufs[key]
 
 
@@ -119,13 +123,20 @@ def _scatter(ctx: _A2AContext, name: str, src_rows: torch.Tensor, plan: _Plan) -
         out[plan.dst_row[ok].long()] = src_rows[ok]
         return out
     if ctx.sym is not None and src_rows.dtype == torch.bfloat16 and h % 8 == 0:
-        buf = ctx.buffer(name, S)
-        view = buf.view(0, (S, h), torch.bfloat16)
-        view.zero_()                      # unused slots must contribute nothing (wgrad sums rows)
-        buf.barrier(0)                    # every rank has cleared its slots
-        buf.handle.a2a_scatter_rows(0, src_rows.contiguous(), plan.dst_rank, plan.dst_row)
-        buf.barrier(1)                    # every rank's rows have landed
-        return view
+        # Ping-pong halves, ONE cross-GPU barrier per call: this call's half was cleared during
+        # the previous call (before its barrier, so every peer's clear is ordered before anybody's
+        # stores of this call); the other half is cleared now for the next call.  Unused slots
+        # must hold zeros (the expert weight gradients sum over all slot rows).  The result is
+        # copied out of symmetric memory: autograd keeps it for the expert wgrad while later
+        # forwards (1F1B, micro-batching) reuse the buffer.
+        entry = ctx.buffer(name, S)
+        buf, use = entry[0], entry[1] & 1
+        entry[1] += 1
+        half = S * h * 2
+        buf.view((1 - use) * half, (S, h), torch.bfloat16).zero_()
+        buf.handle.a2a_scatter_rows(use * half, src_rows.contiguous(), plan.dst_rank, plan.dst_row)
+        buf.barrier(entry[1] & 1)         # every rank's rows have landed (and next halves are clear)
+        return buf.view(use * half, (S, h), torch.bfloat16).clone()
     # fallback: padded dense all_to_all (layout [dst_rank][local_e][src(me)][cap])
     cap, el, ep = plan.capacity, plan.e_local, ctx.ep
     send = src_rows.new_zeros(ep, el, cap, h)
@@ -150,16 +161,19 @@ def _gather(ctx: _A2AContext, name: str, slot_rows: torch.Tensor, plan: _Plan,
         out[ok] = slot_rows[plan.dst_row[ok].long()]
         return out if weight is None else out * weight.reshape(-1, 1).to(out.dtype)
     if ctx.sym is not None and slot_rows.dtype == torch.bfloat16 and h % 8 == 0:
-        buf = ctx.buffer(name, plan.slots_per_rank)
-        view = buf.view(0, (plan.slots_per_rank, h), torch.bfloat16)
-        if not from_symm or slot_rows.data_ptr() != view.data_ptr():
-            view.copy_(slot_rows)
-        buf.barrier(0)                    # all ranks' expert outputs are in place
+        # Ping-pong halves, ONE barrier per call: a half is rewritten two calls later, and every
+        # peer has passed the barrier of the call in between only after its reads of this call.
+        S = plan.slots_per_rank
+        entry = ctx.buffer(name, S)
+        buf, use = entry[0], entry[1] & 1
+        entry[1] += 1
+        half = S * h * 2
+        buf.view(use * half, (S, h), torch.bfloat16).copy_(slot_rows)
+        buf.barrier(entry[1] & 1)         # all ranks' slot rows are in place
         out = torch.empty(n, h, dtype=torch.bfloat16, device=slot_rows.device)
-        buf.handle.a2a_gather_rows(0, out, plan.dst_rank, plan.dst_row,
+        buf.handle.a2a_gather_rows(use * half, out, plan.dst_rank, plan.dst_row,
                                    None if weight is None else weight.reshape(-1).float().contiguous(),
                                    False)
-        buf.barrier(1)                    # peers finished reading before the buffer is re-used
         return out
     cap, el, ep = plan.capacity, plan.e_local, ctx.ep
     send = slot_rows.view(el, ep, cap, h).permute(1, 0, 2, 3).contiguous()      # [src][le][cap]
@@ -190,25 +204,29 @@ class _DispatchFn(torch.autograd.Function):
 class _CombineFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y_slots, weight, a2a, plan):
-        rows = _gather(a2a, "comb_fwd", y_slots.contiguous(), plan, weight, False)
+        # the un-weighted routed rows are kept for the gate-weight gradient (saves a whole
+        # all-to-all in backward); the top-k weighting + sum is a local epilogue
+        y_rows = _gather(a2a, "comb_fwd", y_slots.contiguous(), plan, None, False)
         ctx.a2a, ctx.plan = a2a, plan
-        ctx.save_for_backward(y_slots, weight)
-        return rows.view(plan.T, plan.k, -1).sum(1)
+        ctx.save_for_backward(y_rows, weight)
+        w = weight.reshape(plan.T, plan.k, 1).to(y_rows.dtype)
+        return (y_rows.view(plan.T, plan.k, -1) * w).sum(1)
 
     @staticmethod
     def backward(ctx, d_out):
-        y_slots, weight = ctx.saved_tensors
+        y_rows, weight = ctx.saved_tensors
         plan = ctx.plan
         d_rows = d_out[plan.token]                                 # [T*k, h]
         # d weight = <d_out[token], y_row>
-        y_rows = _gather(ctx.a2a, "comb_bwd_y", y_slots.contiguous(), plan, None, False)
         dw = (d_rows.float() * y_rows.float()).sum(-1).view(plan.T, plan.k)
         scaled = d_rows * weight.reshape(-1, 1).to(d_rows.dtype)
         d_slots = _scatter(ctx.a2a, "comb_bwd", scaled.contiguous(), plan)
-        return d_slots.clone(), dw.to(weight.dtype), None, None
+        return d_slots, dw.to(weight.dtype), None, None
 
 
-_MOE_GROUPED = os.environ.get("TDP_MOE_GROUPED", "0") == "1"
+# all local experts in one grouped tcgen05 launch per product (validated on B200 by
+# scripts/grouped_check.py / tests/test_gpu_kernels.py); TDP_MOE_GROUPED=0 restores the per-expert loop
+_MOE_GROUPED = os.environ.get("TDP_MOE_GROUPED", "1") == "1"
 
 
 class Experts(nn.Module):
@@ -227,7 +245,7 @@ class Experts(nn.Module):
     def forward(self, slots: torch.Tensor) -> torch.Tensor:
         """slots [E_local * rows_per_expert, dim]"""
         if _MOE_GROUPED and grouped.grouped_supported(slots, self.w1, self.w2):
-            # all local experts in one persistent launch per GEMM (opt-in, see ops/grouped.py)
+            # all local experts in one persistent launch per GEMM (ops/grouped.py)
             return grouped.grouped_mlp(slots, self.w1, self.b1, self.w2, self.b2, act="gelu_tanh")
         rows = slots.shape[0] // self.num_local
         outs = []

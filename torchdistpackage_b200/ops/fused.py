@@ -379,3 +379,69 @@ def flatten_module_params(module: torch.nn.Module, align_elems: int = 64):
             v.copy_(p.data)
             p.data = v
     return flat, offs
+
+
+class TensorListTable:
+    """Device-side pointer / numel / dtype tables of a list of (contiguous bf16 / fp32) tensors,
+    for the multi-tensor kernels (one launch for the whole list).  Tables are cached by the
+    tensors' addresses -- gradient lists of a training loop are stable (bucket views)."""
+
+    _cache: dict = {}
+
+    def __init__(self, tensors: List[torch.Tensor]):
+        dev = tensors[0].device
+        self.keep = list(tensors)
+        self.ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=dev)
+        self.numels = torch.tensor([t.numel() for t in tensors], dtype=torch.int64, device=dev)
+        self.dtypes = torch.tensor([0 if t.dtype == torch.bfloat16 else 1 for t in tensors],
+                                   dtype=torch.int32, device=dev)
+
+    @classmethod
+    def of(cls, tensors: List[torch.Tensor]) -> "TensorListTable":
+        key = tuple((t.data_ptr(), t.numel(), t.dtype) for t in tensors)
+        tab = cls._cache.get(key)
+        if tab is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            tab = cls._cache[key] = cls(tensors)
+        return tab
+
+
+def _multi_ok(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.is_contiguous() and t.dtype in (torch.bfloat16, torch.float32)
+
+
+def multi_sumsq(tensors: List[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum_i ||t_i||^2 as a 1-element fp32 device tensor: ONE kernel launch for all supported
+    tensors (csrc/fused/optim.cu ``sumsq_multi_kernel``), torch fallback for the rest."""
+    tensors = [t for t in tensors if t.numel() > 0]
+    dev = tensors[0].device if tensors else torch.device("cpu")
+    acc = out if out is not None else torch.zeros(1, dtype=torch.float32, device=dev)
+    C = native() if dev.type == "cuda" else None
+    fast = [t for t in tensors if C is not None and _multi_ok(t)]
+    if fast:
+        tab = TensorListTable.of(fast)
+        C.sumsq_multi(tab.ptrs, tab.numels, tab.dtypes, acc)
+    for t in tensors:
+        if C is None or not _multi_ok(t):
+            acc += t.detach().float().pow(2).sum()
+    return acc
+
+
+def multi_scale_(tensors: List[torch.Tensor], scale: float = 1.0,
+                 scale_t: Optional[torch.Tensor] = None) -> None:
+    """t_i *= scale (* scale_t[0], a device scalar -- no host sync) for every tensor, one launch."""
+    tensors = [t for t in tensors if t.numel() > 0]
+    if not tensors:
+        return
+    dev = tensors[0].device
+    C = native() if dev.type == "cuda" else None
+    fast = [t for t in tensors if C is not None and _multi_ok(t)]
+    if fast:
+        tab = TensorListTable.of(fast)
+        C.scale_multi(tab.ptrs, tab.numels, tab.dtypes, float(scale),
+                      None if scale_t is None else scale_t.reshape(1).float())
+    for t in tensors:
+        if C is None or not _multi_ok(t):
+            f = scale if scale_t is None else scale_t.to(t.dtype) * scale
+            t.detach().mul_(f)

@@ -230,6 +230,15 @@ class SymmGroup:
         if native() is None:
             self.reason = "native extension missing"
             return
+        # Peer mappings / NVLS multicast only exist inside one NVSwitch domain: every rank of
+        # the group must sit on the same host (boot id) and see every peer device.  The check is
+        # a collective, so all ranks agree and cross-node groups (e.g. the inter-node DDP group of
+        # hybrid ZeRO, or DP across nodes under TP=8) fall back to NCCL instead of hanging in the
+        # handle exchange.
+        why = self._locality_problem()
+        if why:
+            self.reason = why
+            return
         try:
             import torch.distributed._symmetric_memory as symm_mem
             try:
@@ -244,6 +253,44 @@ class SymmGroup:
         except Exception as e:  # pragma: no cover - depends on the torch build
             self.reason = f"symmetric memory unavailable: {e}"
 
+    def _locality_problem(self) -> str:
+        host = _host_identity()
+        dev = torch.cuda.current_device()
+        try:
+            uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        except Exception:
+            uuid = f"{host}:{dev}"
+        infos = [None] * self.world
+        try:
+            dist.all_gather_object(infos, (host, uuid), group=self.pg)
+        except Exception as e:  # pragma: no cover
+            return f"locality exchange failed: {e}"
+        problem = ""
+        if len({h for h, _ in infos}) != 1:
+            problem = "group spans more than one host (no NVSwitch peer access)"
+        elif len({u for _, u in infos}) != len(infos):
+            problem = "two ranks of the group share a device"
+        else:
+            # peers this process can see (no CUDA_VISIBLE_DEVICES mask): ask the driver
+            local = {}
+            for i in range(torch.cuda.device_count()):
+                try:
+                    local[str(torch.cuda.get_device_properties(i).uuid)] = i
+                except Exception:
+                    pass
+            for _, u in infos:
+                d = local.get(u)
+                if d is not None and d != dev and not torch.cuda.can_device_access_peer(dev, d):
+                    problem = f"device {dev} cannot access peer device {d}"
+                    break
+        # agree on the outcome: one rank's failure disables the path everywhere
+        flags = [None] * self.world
+        dist.all_gather_object(flags, problem, group=self.pg)
+        for f in flags:
+            if f:
+                return f
+        return ""
+
     def alloc(self, nbytes: int) -> SymmBuffer:
         if not self.enabled:
             raise RuntimeError(f"symmetric memory not available for this group: {self.reason}")
@@ -251,6 +298,16 @@ class SymmGroup:
         buf = SymmBuffer(self, nbytes)
         self._buffers.append(buf)
         return buf
+
+
+def _host_identity() -> str:
+    """Stable per-boot identity of this host (containers on one box share it)."""
+    try:
+        with open("/proc/sys/kernel/random/boot_id") as f:
+            return f.read().strip()
+    except OSError:
+        import socket
+        return socket.gethostname()
 
 
 _GROUP_CACHE: Dict[int, SymmGroup] = {}

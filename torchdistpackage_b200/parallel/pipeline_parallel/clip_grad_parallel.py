@@ -39,13 +39,8 @@ def _sum_pow(grads, norm_type: float, device) -> torch.Tensor:
         return total
     C = native() if device.type == "cuda" else None
     if norm_type == 2.0 and C is not None:
-        acc = torch.zeros(1, dtype=torch.float32, device=device)
-        for g in grads:
-            if g.dtype in (torch.bfloat16, torch.float32) and g.is_contiguous():
-                C.sumsq(g, acc)
-            else:
-                acc += g.float().pow(2).sum()
-        return acc[0]
+        from ...ops.fused import multi_sumsq
+        return multi_sumsq(list(grads))[0]          # one launch for the whole list
     for g in grads:
         total = total + g.detach().float().abs().pow(norm_type).sum()
     return total
@@ -76,10 +71,13 @@ def clip_grad_norm_(parameters: _TensorOrTensors, max_norm: float, norm_type: fl
         total_norm = local
     else:
         if zero_optimizer is not None:
-            # ZeRO: every element of the (replicated-over-TP-or-not) model lives in exactly one
-            # data-parallel shard
-            sq = zero_optimizer.local_grad_sq_norm() if norm_type == 2.0 else None
-            assert sq is not None, "ZeRO clipping supports the L2 norm"
+            # ZeRO: every element of this rank's model lives in exactly one data-parallel shard.
+            # Under tensor parallelism the sum over the tensor group must count tensor-parallel
+            # *shards* on every TP rank but parameters that are *replicated* over TP (LayerNorm,
+            # row-parallel bias, ...) only once: TP ranks other than the first leave them out.
+            assert norm_type == 2.0, "ZeRO clipping supports the L2 norm"
+            sq = zero_optimizer.local_grad_sq_norm(
+                include=None if (not tp_on or tp_first) else _is_tp_shard)
             if zero_optimizer.world > 1:
                 dist.all_reduce(sq, group=zero_optimizer.group)
             total = sq
@@ -105,13 +103,12 @@ def clip_grad_norm_(parameters: _TensorOrTensors, max_norm: float, norm_type: fl
     clip_coef = torch.clamp(max_norm / (total_norm + 1e-6), max=1.0)
     if zero_optimizer is not None:
         zero_optimizer.scale_master_grads(clip_coef)
-    C = native() if device.type == "cuda" else None
-    for p in params:
-        g = p.grad
-        if C is not None and g.is_contiguous() and g.dtype in (torch.bfloat16, torch.float32):
-            C.scale_(g, 1.0, clip_coef.reshape(1).float())
-        else:
-            g.detach().mul_(clip_coef.to(g.dtype))
+    if device.type == "cuda" and native() is not None:
+        from ...ops.fused import multi_scale_
+        multi_scale_([p.grad for p in params], 1.0, clip_coef)     # one launch, no host sync
+    else:
+        for p in params:
+            p.grad.detach().mul_(clip_coef.to(p.grad.dtype))
     return total_norm
 
 

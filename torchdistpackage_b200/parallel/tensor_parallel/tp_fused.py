@@ -172,7 +172,9 @@ def _gemm_ar(ctx: FusedSpContext, name: str, a: torch.Tensor, w: torch.Tensor, t
     """out_full [T, N] = all_reduce(a @ op(w)) + bias, fused: the GEMM epilogue scatters tiles to
     the chunk owners (as in GEMM->RS); each owner's reduce kernel then *broadcasts* its reduced
     rows to every rank with ``multimem.st`` (two-shot all-reduce whose first shot is the GEMM
-    epilogue).  Returns a view of the symmetric output buffer (valid until the call after next)."""
+    epilogue).  The result is copied out of the (reused) symmetric output buffer: autograd may
+    keep it across several forwards of the same module (1F1B warm-up, forward-all-then-backward
+    micro-batching), during which the buffer is overwritten."""
     T, _ = a.shape
     rows = T // ctx.tp
     N = w.shape[0] if trans_b else w.shape[1]
@@ -185,7 +187,7 @@ def _gemm_ar(ctx: FusedSpContext, name: str, a: torch.Tensor, w: torch.Tensor, t
     buf.handle.rs_reduce(off, rows, N, reg.flag_word, target, bias, None, None, True, off + nb,
                          True, 0)
     buf.barrier(0)                           # every owner's broadcast has landed everywhere
-    return buf.view(off + nb, (T, N), torch.bfloat16)
+    return buf.view(off + nb, (T, N), torch.bfloat16).clone()
 
 
 class _LinearArFn(torch.autograd.Function):

@@ -99,7 +99,11 @@ class Transformer(nn.Module):
         for blk in self.blocks:
             x = blk(x)
         if self.sequence_parallel:
-            x = gather_from_sequence_parallel_region(x)
+            # the gathered output feeds *replicated* compute (every TP rank evaluates the same
+            # loss on it), so its gradient is identical on all ranks: backward splits it instead of
+            # reduce-scattering (which would sum tp identical copies and make every gradient of the
+            # stack tp times too large -- the reference does that, transformer.py:96-99)
+            x = gather_from_sequence_parallel_region(x, tensor_parallel_output_grad=False)
         return x
 
 
