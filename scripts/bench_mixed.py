@@ -131,8 +131,9 @@ inputs = ([tokens] if first else []) + ([targets] if last else [])
 
 
 def step():
+    kw = {"static_shapes": True} if args.impl == "ours" else {}   # (the reference re-handshakes)
     out = forward_backward(opt, fwd_fn, None, inputs or None, num_microbatches=args.micro,
-                           dtype=torch.bfloat16)
+                           dtype=torch.bfloat16, **kw)
     post_backward()
     opt.step()
     return out

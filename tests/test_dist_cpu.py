@@ -335,6 +335,48 @@ def test_pipeline_1f1b_matches_serial(pp, n_micro):
     run_distributed(_w_pipeline, pp, pp, n_micro)
 
 
+def _w_pipeline_static_shapes(rank, world):
+    """static_shapes=True: the shape handshake happens on the first call only; later calls must
+    give the same results without any metadata message."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import forward_backward
+    from torchdistpackage_b200.parallel.pipeline_parallel import comm, pipeline_sched
+    tdp.tpc.setup_process_groups([("pipe", world)])
+    tdp.fix_rand(0)
+    layers = [nn.Linear(8, 8) for _ in range(world)]
+    mine = layers[rank]
+    first, last = rank == 0, rank == world - 1
+    x = torch.randn(8, 8)
+
+    def fwd(inp):
+        h = mine(inp[0] if isinstance(inp, (list, tuple)) else inp)
+        return h.pow(2).mean() if last else h
+
+    calls = {"n": 0}
+    orig = comm.send_obj_meta
+
+    def counting(obj, need_meta=True, next_rank=None):
+        if need_meta:
+            calls["n"] += 1
+        return orig(obj, need_meta, next_rank)
+    comm.send_obj_meta = counting
+    pipeline_sched.clear_shape_cache()
+    outs = []
+    for it in range(3):
+        mine.zero_grad()
+        out = forward_backward(None, fwd, None, x if first else None, num_microbatches=4,
+                               dtype=torch.float32, static_shapes=True)
+        outs.append(float(out.detach()) if last else 0.0)
+    comm.send_obj_meta = orig
+    assert calls["n"] == (0 if last else 1), calls          # handshake only on the first call
+    if last:
+        assert abs(outs[0] - outs[1]) < 1e-7 and abs(outs[1] - outs[2]) < 1e-7
+
+
+def test_pipeline_static_shapes_skip_the_handshake():
+    run_distributed(_w_pipeline_static_shapes, 3)
+
+
 def test_pipeline_with_data_parallel():
     run_distributed(_w_pipeline, 4, 2, 2)
 

@@ -251,14 +251,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
           while (a_loc[0] < it.n_sub[0] || b_loc[0] < it.n_sub[0] || a_loc[1] < it.n_sub[1] ||
                  b_loc[1] < it.n_sub[1]) {
             for (int w = 0; w < 2; ++w) {
-              if (a_loc[w] < it.n_sub[w] && mbar_try_wait(&s_free[w], a_cnt[w] & 1)) {
+              if (a_loc[w] < it.n_sub[w] && mbar_test_wait(&s_free[w], a_cnt[w] & 1)) {
                 const int j = a_loc[w];
                 const uint32_t gj = g + j + 1;
                 if (j + 1 >= it.n_sub[w]) {
                   ++a_cnt[w];
                   ++a_loc[w];
-                } else if (mbar_try_wait(&k_full[gj % kStages], (gj / kStages) & 1) &&
-                           mbar_try_wait(&v_full[gj % kStages], (gj / kStages) & 1)) {
+                } else if (mbar_test_wait(&k_full[gj % kStages], (gj / kStages) & 1) &&
+                           mbar_test_wait(&v_full[gj % kStages], (gj / kStages) & 1)) {
                   ++a_cnt[w];
                   ++a_loc[w];
                   tc_fence_after();
@@ -267,7 +267,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,    // box {
                   release();
                 }
               }
-              if (b_loc[w] < it.n_sub[w] && mbar_try_wait(&p_ready[w], b_cnt[w] & 1)) {
+              if (b_loc[w] < it.n_sub[w] && mbar_test_wait(&p_ready[w], b_cnt[w] & 1)) {
                 ++b_cnt[w];
                 const int j = b_loc[w];
                 tc_fence_after();

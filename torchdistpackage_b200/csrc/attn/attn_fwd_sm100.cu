@@ -7,7 +7,7 @@
 //   warp  8      TMA producer  (Q tiles per work item; K(j), V(j) through a 3-stage ring each)
 //   warp  9      MMA issuer    (one elected thread) + TMEM allocation
 //   warps 10-11  idle (they only exist so that warps 8-11 form a warp-group for setmaxnreg:
-//                the two softmax groups run with 224 registers, the rest with 56)
+//                the two softmax groups run with 216 registers, the rest with 72: (168-72)*128 = (216-168)*256 registers change hands)
 //
 //   work item = (batch b, head h, 256 query rows); one CTA per SM walks a static, heavy-first
 //   "snake" schedule over all items (causal tiles differ 5x in work), so set-up cost (TMEM
@@ -58,12 +58,12 @@ constexpr uint32_t kTmemColsAttn = 512;                  // S0 | S1 | O0 | O1 (3
 constexpr float kRescaleThreshold = 8.f;                 // log2 units
 
 struct AttnSmem {
-  static constexpr int kQ = 0;                                   // 2 tiles
-  static constexpr int kK = kQ + 2 * kTileBytes;                 // kStagesKV tiles
+  static constexpr int kQ = 0;                                   // 2 buffers x 2 tiles
+  static constexpr int kK = kQ + 4 * kTileBytes;                 // kStagesKV tiles
   static constexpr int kV = kK + kStagesKV * kTileBytes;         // kStagesKV tiles
   static constexpr int kP = kV + kStagesKV * kTileBytes;         // 2 P tiles
   static constexpr int kBars = kP + 2 * kPBytes;
-  static constexpr int kTotal = kBars + 256;                     // 196 864 B
+  static constexpr int kTotal = kBars + 256;                     // 229 632 B
 };
 
 struct AttnParams {
@@ -115,9 +115,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
   uint8_t* smem_v = smem + AttnSmem::kV;
   uint8_t* smem_p = smem + AttnSmem::kP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::kBars);
-  uint64_t* q_full = bars;                       // 1
-  uint64_t* q_empty = bars + 1;                  // 1: every S MMA of the item has completed
-  uint64_t* k_full = bars + 2;                   // kStagesKV
+  uint64_t* q_full = bars;                       // 2 (Q tiles of item `round` live in buffer round & 1)
+  uint64_t* q_empty = bars + 2;                  // 2: every S MMA of the item has completed
+  uint64_t* k_full = bars + 4;                   // kStagesKV
   uint64_t* k_empty = k_full + kStagesKV;
   uint64_t* v_full = k_empty + kStagesKV;
   uint64_t* v_empty = v_full + kStagesKV;
@@ -135,8 +135,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
     for (int i = 0; i < kStagesKV; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -159,7 +161,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp_idx >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp_idx == 8) {
       // ================================ TMA producer ================================
       if (elect_one()) {
@@ -167,11 +169,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
         Item it;
         for (int round = 0; get_item(p, round, it); ++round) {
           const int row_base = it.b * p.T;
-          if (round > 0) mbar_wait(q_empty, (round - 1) & 1);
+          // Q is double buffered: the next item's query tiles load while this item computes
+          const int qb = round & 1;
+          if (round >= 2) mbar_wait(&q_empty[qb], ((round >> 1) - 1) & 1);
           const int n_q = it.n_kv[1] > 0 ? 2 : 1;
-          mbar_expect_tx(q_full, n_q * kTileBytes);
+          mbar_expect_tx(&q_full[qb], n_q * kTileBytes);
           for (int w = 0; w < n_q; ++w)
-            tma_load_2d(&tmap_q, q_full, smem_q + w * kTileBytes, it.h * kHeadDim,
+            tma_load_2d(&tmap_q, &q_full[qb], smem_q + (2 * qb + w) * kTileBytes, it.h * kHeadDim,
                         row_base + it.q0 + w * kTileQ);
           for (int j = 0; j < it.n_max; ++j, ++g) {
             const int st = g % kStagesKV;
@@ -196,8 +200,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
       const uint32_t idesc_s = make_idesc_bf16_f32(kTileQ, kTileKV, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16_f32(kTileQ, kHeadDim, 0, 1);
       constexpr uint32_t kUmmaKBytes = 16 * 2;          // K = 16 bf16 along a 128-byte swizzled row
+      int qbuf = 0;
       auto issue_s = [&](int w, int st) {
-        const uint32_t sa = smem_u32(smem_q + w * kTileBytes);
+        const uint32_t sa = smem_u32(smem_q + (2 * qbuf + w) * kTileBytes);
         const uint32_t sb = smem_u32(smem_k + st * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k) {
@@ -254,11 +259,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
               ++rv;
             }
             if (!q_released && s_iss[0] >= it.n_kv[0] && s_iss[1] >= it.n_kv[1]) {
-              umma_commit(q_empty);                            // last S of the item issued
+              umma_commit(&q_empty[qbuf]);                     // last S of the item issued
               q_released = true;
             }
           };
-          mbar_wait(q_full, round & 1);
+          qbuf = round & 1;
+          mbar_wait(&q_full[qbuf], (round >> 1) & 1);
           mbar_wait(&k_full[g % kStagesKV], (g / kStagesKV) & 1);
           tc_fence_after();
           for (int w = 0; w < 2; ++w)
@@ -269,13 +275,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
             for (int w = 0; w < 2; ++w) {
               // an event is only consumed when the K / V stage it needs has landed: a blocking
               // wait here could starve the other group, whose progress frees ring stages
-              if (a_loc[w] < it.n_kv[w] && mbar_try_wait(&s_free[w], a_cnt[w] & 1)) {
+              if (a_loc[w] < it.n_kv[w] && mbar_test_wait(&s_free[w], a_cnt[w] & 1)) {
                 const int j = a_loc[w];
                 const uint32_t gj = g + j + 1;
                 if (j + 1 >= it.n_kv[w]) {
                   ++a_cnt[w];
                   ++a_loc[w];
-                } else if (mbar_try_wait(&k_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
+                } else if (mbar_test_wait(&k_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
                   ++a_cnt[w];
                   ++a_loc[w];
                   tc_fence_after();
@@ -284,10 +290,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
                   release();
                 }
               }
-              if (b_loc[w] < it.n_kv[w] && mbar_try_wait(&p_ready[w], b_cnt[w] & 1)) {
+              if (b_loc[w] < it.n_kv[w] && mbar_test_wait(&p_ready[w], b_cnt[w] & 1)) {
                 const int j = b_loc[w];
                 const uint32_t gj = g + j;
-                if (mbar_try_wait(&v_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
+                if (mbar_test_wait(&v_full[gj % kStagesKV], (gj / kStagesKV) & 1)) {
                   ++b_cnt[w];
                   tc_fence_after();
                   issue_pv(w, gj % kStagesKV, j > 0);
@@ -304,7 +310,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
     }
   } else {
     // ================================ softmax warp-groups ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int wg = warp_idx >> 2;
     const int quad = warp_idx & 3;
     const int row = quad * 32 + lane;                       // row in the 128-row tile = TMEM lane
@@ -339,13 +345,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box {64, 
           for (int i = 0; i < kTileKV; ++i)
             if (i > row) r[i] = 0xff800000u;                // -inf
         }
-        float mx0 = __uint_as_float(r[0]), mx1 = __uint_as_float(r[1]);
+        // 8 independent 3-input max chains (a single chain would be 63 dependent ops)
+        float mx[8];
 #pragma unroll
-        for (int i = 2; i < kTileKV; i += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-          if (i + 3 < kTileKV) mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        for (int c = 0; c < 8; ++c)
+          mx[c] = fmax3(__uint_as_float(r[3 * c]), __uint_as_float(r[3 * c + 1]),
+                        __uint_as_float(r[3 * c + 2]));
+#pragma unroll
+        for (int i = 24; i + 15 < kTileKV; i += 16) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            mx[c] = fmax3(mx[c], __uint_as_float(r[i + 2 * c]), __uint_as_float(r[i + 2 * c + 1]));
         }
-        const float sm = fmaxf(mx0, mx1) * p.scale_log2;
+        // 24 + 6*16 = 120: the last 8 columns
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], __uint_as_float(r[120 + c]));
+        const float sm = fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]),
+                               fmaxf(mx[6], mx[7])) * p.scale_log2;
         if (j == 0) {
           m_run = sm;
         } else if (__any_sync(0xffffffffu, sm > m_run + kRescaleThreshold)) {

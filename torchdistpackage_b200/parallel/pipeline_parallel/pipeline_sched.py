@@ -72,11 +72,29 @@ def _shapes_of(obj):
     return [t.shape for t in obj]
 
 
+_SHAPE_CACHE: dict = {}      # static_shapes=True: (config key) -> (ft_shapes, bt_shapes)
+
+
+def clear_shape_cache() -> None:
+    _SHAPE_CACHE.clear()
+
+
 def forward_backward(optimizer, fwd_fn: Callable, bwd_fn: Optional[Callable], inputs,
                      num_microbatches: int = 1, forward_only: bool = False,
-                     dtype: torch.dtype = torch.bfloat16, scatter_gather_tensors: bool = False):
+                     dtype: torch.dtype = torch.bfloat16, scatter_gather_tensors: bool = False,
+                     static_shapes: Optional[bool] = None):
     """Run one mini-batch through this pipeline stage.  Returns the last micro-batch's output
-    (the loss on the last stage)."""
+    (the loss on the last stage).
+
+    ``static_shapes=True`` (or ``TDP_PP_STATIC_SHAPES=1``): the caller promises that, for a given
+    ``(num_microbatches, mini-batch size, dtype)``, the activations exchanged between stages have
+    the same shapes on every call (the usual case in training).  The shape handshake -- a blocking
+    metadata message plus a host read-back per call (reference comm.py:26-105 repeats it on every
+    call) -- is then done once and cached, so steady-state steps issue no blocking communication
+    and no host synchronisation.  All stages must pass the same setting."""
+    if static_shapes is None:
+        import os
+        static_shapes = os.environ.get("TDP_PP_STATIC_SHAPES", "0") == "1"
     pp_size = tpc.get_group_size("pipe")
     pp_rank = tpc.get_group_rank("pipe")
     first = tpc.is_first_in_pipeline_group()
@@ -99,6 +117,17 @@ def forward_backward(optimizer, fwd_fn: Callable, bwd_fn: Optional[Callable], in
     bt_shapes = None          # shapes of the grads coming back = shapes of what we send forward
     need_send_meta = True
     output_obj = None
+    cache_key = None
+    if static_shapes:
+        # every stage derives the same key from information all stages share: the schedule
+        # (micro-batch count), the pipe group and the dtype; the first stage's batch size reaches
+        # later stages only through the shapes themselves, hence the caller's promise above
+        cache_key = (id(tpc.get_group("pipe")), int(num_microbatches), str(dtype), bool(sg),
+                     bool(forward_only))
+        hit = _SHAPE_CACHE.get(cache_key)
+        if hit is not None:
+            ft_shapes, bt_shapes = hit
+            need_send_meta = False
 
     if optimizer is not None:
         optimizer.zero_grad()
@@ -159,6 +188,8 @@ def forward_backward(optimizer, fwd_fn: Callable, bwd_fn: Optional[Callable], in
             output_grad = comm.recv_backward(bt_shapes, dtype=dtype, scatter_gather_tensors=sg)
             input_grad = _backward_step(in_b, out_b, output_grad, bwd_fn)
             comm.send_backward(input_grad, scatter_gather_tensors=sg)
+    if cache_key is not None and cache_key not in _SHAPE_CACHE:
+        _SHAPE_CACHE[cache_key] = (ft_shapes, bt_shapes)
     return output_obj
 
 
