@@ -123,14 +123,14 @@ cudaError_t launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   return cudaGetLastError();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 2>
 cudaError_t launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t_in,
                         const CUtensorMap& t_aux, const CUtensorMap& tc, const GemmParams& p,
                         int grid, cudaStream_t stream) {
-  using S = Gemm2CtaSmem<BLOCK_N>;
+  using S = Gemm2CtaSmem<BLOCK_N, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_sm100_2cta_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_sm100_2cta_kernel<BLOCK_N, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::kTotalBytes);
     if (e != cudaSuccess) return e;
@@ -149,7 +149,7 @@ cudaError_t launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_2cta_kernel<BLOCK_N>, ta, tb, t_in, t_aux, tc, p);
+  return cudaLaunchKernelEx(&cfg, gemm_bf16_sm100_2cta_kernel<BLOCK_N, EPI>, ta, tb, t_in, t_aux, tc, p);
 }
 
 }  // namespace
@@ -372,7 +372,15 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
   // slower with the heavy GELU epilogues.  TDP_GEMM_2CTA=0/1 forces the choice.
   static const int env_2cta = [] { const char* v = getenv("TDP_GEMM_2CTA"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
   bool auto_2cta = g.K >= 2048 && g.act == ACT_NONE && g.aux_out == nullptr;
-  if (env_2cta >= 0) auto_2cta = env_2cta == 1;
+  // short-K products with a heavy fused epilogue (GELU + pre-activation output, GELU' x gradient,
+  // residual): the pair kernel's variant with four operand stages and a six-deep epilogue staging
+  // ring (gemm_sm100_2cta.cuh).  TDP_GEMM_EPIRING=0 keeps them on the 1-CTA kernel.
+  static const int env_ring = [] { const char* v = getenv("TDP_GEMM_EPIRING"); return v ? (v[0] == '1' ? 1 : 0) : -1; }();
+  const bool heavy_epi = (g.act != ACT_NONE || g.aux_out != nullptr || p.epi_in_tma != 0) &&
+                         g.K <= 1536 && g.N >= 512 && g.M >= 1024 && g.block_n != 128;
+  const bool epi_ring = env_ring >= 0 ? (env_ring == 1 && heavy_epi) : heavy_epi;
+  if (epi_ring && g.cta_group != 1) auto_2cta = true;
+  if (env_2cta >= 0 && !epi_ring) auto_2cta = env_2cta == 1;
   if (g.grp_rows == 0 && (g.cta_group == 2 || (g.cta_group == 0 && auto_2cta)) && p.comm_mode == COMM_NONE &&
       p.split_k == 1 && p.use_tma_store && g.N > 128 && g.M > 128) {
     GemmParams q = p;
@@ -380,7 +388,8 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     const int clusters = (max_ctas & ~1) / 2;
     // pair tile 256 x 256, or 256 x 128 when the wide tiles cannot occupy every CTA pair
     int bn2 = g.block_n == 128 ? 128 : 256;
-    if (g.block_n == 0 && static_cast<long>(q.num_m_blocks) * ((g.N + 255) / 256) < clusters) bn2 = 128;
+    if (g.block_n == 0 && !epi_ring &&
+        static_cast<long>(q.num_m_blocks) * ((g.N + 255) / 256) < clusters) bn2 = 128;
     q.num_n_blocks = (g.N + bn2 - 1) / bn2;
     q.group_m = 4;
     CUtensorMap tb2 = tb;
@@ -390,8 +399,10 @@ int launch_gemm_bf16(const GemmLaunch& g, cudaStream_t stream, const char** err)
     }
     const long tiles2 = static_cast<long>(q.num_m_blocks) * q.num_n_blocks;
     const int ctas = static_cast<int>(tiles2 < clusters ? tiles2 : clusters) * 2;
-    cudaError_t e2 = bn2 == 256 ? launch_2cta<256>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream)
-                                : launch_2cta<128>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream);
+    cudaError_t e2 = bn2 == 256
+        ? (epi_ring ? launch_2cta<256, 6>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream)
+                    : launch_2cta<256>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream))
+        : launch_2cta<128>(ta, tb2, t_in, t_aux, sm.m[0], q, ctas, stream);
     if (e2 != cudaSuccess) {
       snprintf(msg, sizeof(msg), "gemm 2cta launch: %s", cudaGetErrorString(e2));
       return static_cast<int>(e2);

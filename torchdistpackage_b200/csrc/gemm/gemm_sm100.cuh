@@ -187,10 +187,20 @@ TDP_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); 
 // `in_row` (optional): this thread's row of the TMA-loaded, 128B-swizzled input sub-tile (residual
 // or dGELU pre-activation) -- chunk c of the 64-column sub-tile lives at (c ^ swz) * 16.
 // `z_row` (optional): same layout, receives the pre-activation copy instead of a global store.
+// `bias_s` (optional): the 32 bias values of these columns, staged in shared memory.
 TDP_DEVICE void epilogue_math(const GemmParams& p, f32x2 (&v)[16], int row, int col0, bool full,
                               const uint8_t* in_row = nullptr, uint8_t* z_row = nullptr, int h = 0,
-                              int swz = 0) {
-  if (p.bias != nullptr) {
+                              int swz = 0, const __nv_bfloat16* bias_s = nullptr) {
+  if (bias_s != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 b = *reinterpret_cast<const uint4*>(bias_s + 8 * j);     // warp-wide broadcast
+      v[4 * j] = add2(v[4 * j], bf16x2_to_f32x2(b.x));
+      v[4 * j + 1] = add2(v[4 * j + 1], bf16x2_to_f32x2(b.y));
+      v[4 * j + 2] = add2(v[4 * j + 2], bf16x2_to_f32x2(b.z));
+      v[4 * j + 3] = add2(v[4 * j + 3], bf16x2_to_f32x2(b.w));
+    }
+  } else if (p.bias != nullptr) {
     // grouped GEMM: one bias vector per group (expert) of output rows
     const __nv_bfloat16* bias =
         p.bias + (p.grp_mblocks > 0 ? (row / (p.grp_mblocks * kBlockM)) * p.grp_bias : 0);

@@ -55,7 +55,10 @@ TDP_DEVICE void umma_commit_2sm(uint64_t* bar) {
 }
 // arrive on the leader CTA's copy of a barrier (works from either CTA)
 TDP_DEVICE void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+  // relaxed: what is handed over is a TMEM accumulator stage, already ordered by
+  // tcgen05.wait::ld + tcgen05.fence::before_thread_sync -- a cluster-scope *release* would also
+  // drain this warp's outstanding shared-memory stores (an ERRBAR per warp and tile)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
                    smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
@@ -73,30 +76,44 @@ TDP_DEVICE void tmem_dealloc_2sm(uint32_t taddr) {
                : "memory");
 }
 
-template <int BLOCK_N_>
+// kEpiBufs = number of 16 KiB epilogue staging buffers.  2: the main loop gets the shared memory
+// (6 / 8 operand stages) -- right for long-K products.  6 (256-wide tiles only): 4 operand stages
+// and a six-deep staging ring, for short-K products with a heavy fused epilogue (GELU + second
+// output, GELU' x gradient, residual), where the chain "row-wise input TMA load -> math -> TMA
+// store" of one 64-column sub-tile is longer than the sub-tile's share of the MMA time: with two
+// buffers every sub-tile waits for the previous store to be read out and for its own input to
+// land; with six, inputs are prefetched three sub-tiles ahead (across tile boundaries) and up to
+// three stores are in flight.
+template <int BLOCK_N_, int kEpiBufs_ = 2>
 struct Gemm2CtaSmem {
   static constexpr int kBlockN = BLOCK_N_;                         // per CTA pair: 256 or 128
+  static constexpr int kStoreBufs = kEpiBufs_;
   static constexpr int kStageBytesA = kBlockM * kBlockK * 2;       // 16 KiB (my 128 rows)
   static constexpr int kStageBytesB = (kBlockN / 2) * kBlockK * 2; // 16 / 8 KiB (my half of N)
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = kBlockN == 256 ? 6 : 8;
-  static constexpr int kStoreStageBytes = 2 * kStoreBytes;
+  static constexpr int kStages = kBlockN == 256 ? (kEpiBufs_ == 2 ? 6 : 4) : 8;
+  static constexpr int kStoreStageBytes = kStoreBufs * kStoreBytes;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotalBytes = kStages * kStageBytes + kStoreStageBytes + kBarrierBytes;
+  static constexpr int kBiasBytes = 2 * kBlockN * 2;      // bias of the current / next tile's columns
+  static constexpr int kTotalBytes =
+      kStages * kStageBytes + kStoreStageBytes + kBarrierBytes + kBiasBytes;
+  static_assert(kEpiBufs_ == 2 || kEpiBufs_ == 6, "staging ring depth");
 };
 
 // p.num_m_blocks counts 256-row blocks here; p.num_n_blocks BLOCK_N-column blocks.
 // BLOCK_N = 128 gives 256 x 128 pair tiles: twice as many tiles for weight-gradient shaped
 // products (few output tiles, long K) that would otherwise leave half of the machine idle.
-template <int BLOCK_N>
+template <int BLOCK_N, int kEpiBufs = 2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             const __grid_constant__ CUtensorMap tmap_b,
                             const __grid_constant__ CUtensorMap tmap_in,
                             const __grid_constant__ CUtensorMap tmap_aux,
                             const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
-  using S = Gemm2CtaSmem<BLOCK_N>;
+  using S = Gemm2CtaSmem<BLOCK_N, kEpiBufs>;
   constexpr int kStages = S::kStages;
+  constexpr int NB = S::kStoreBufs;          // staging ring depth
+  constexpr int kPrefetch = NB / 2;          // row-wise inputs are loaded this many sub-tiles ahead
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -110,8 +127,10 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
-  uint64_t* in_bar = bars + 2 * kStages + 4;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+  uint64_t* in_bar = bars + 2 * kStages + 4;                     // NB
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + NB);
+  __nv_bfloat16* smem_bias =
+      reinterpret_cast<__nv_bfloat16*>(smem_store + S::kStoreStageBytes + S::kBarrierBytes);
 
   const int warp_idx = threadIdx.x / 32;
   const uint32_t cta_rank = cluster_ctarank();
@@ -130,8 +149,8 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 2 * kNumEpilogueWarps);   // epilogue warps of both CTAs
-      mbar_init(&in_bar[i], 1);
     }
+    for (int i = 0; i < NB; ++i) mbar_init(&in_bar[i], 1);
     fence_barrier_init();
   } else if (warp_idx == 1) {
     tmem_alloc_2sm<kTmemCols>(tmem_holder);
@@ -232,8 +251,36 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool aux_tma = p.epi_aux_tma != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int store_buf = 0;
-    uint32_t in_phase = 0;
+    // The staging buffers form a ring indexed by the running sub-tile number q (it keeps counting
+    // across tiles).  plain: buffer q % NB, a store may be read out while NB-1 newer ones are
+    // queued.  aux (two outputs per sub-tile): buffer pairs, NB/2-1 newer groups.  in (row-wise
+    // input): input(q + kPrefetch) is loaded into buffer (q + kPrefetch) % NB as soon as
+    // store(q + kPrefetch - NB) has been read out, i.e. with NB-kPrefetch-1 newer groups pending.
+    uint32_t q = 0;
+    uint32_t in_phase = 0;                       // phase bit per in_bar
+    // issuer only: prefetch cursor, kPrefetch sub-tiles ahead of the compute cursor
+    int pf_tile = cluster_id, pf_sub = 0;
+    uint32_t pf_q = 0;
+    auto pf_issue = [&]() {
+      if (pf_tile >= num_tiles) return;
+      int pm, pn;
+      tile_to_mn(p, pf_tile, pm, pn);
+      const int pm0 = pm * 2 * kBlockM + static_cast<int>(cta_rank) * kBlockM;
+      const int pn0 = pn * BLOCK_N;
+      const int pns = (min(BLOCK_N, p.N - pn0) + kStoreCols - 1) / kStoreCols;
+      const int b = static_cast<int>(pf_q % NB);
+      mbar_expect_tx(&in_bar[b], kStoreBytes);
+      tma_load_2d(&tmap_in, &in_bar[b], smem_store + b * kStoreBytes, pn0 + pf_sub * kStoreCols, pm0);
+      ++pf_q;
+      if (++pf_sub == pns) {
+        pf_sub = 0;
+        pf_tile += num_clusters;
+      }
+    };
+    if (in_tma && issuer) {
+#pragma unroll 1
+      for (int i = 0; i < kPrefetch; ++i) pf_issue();      // the ring is empty: no wait needed
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m_blk, n_blk;
       tile_to_mn(p, tile, m_blk, n_blk);
@@ -244,37 +291,44 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const bool row_ok = row < p.M;
       const int swz = row_in_tile & 7;
 
+      // bias of this tile's columns -> smem while the MMAs still run (a global load per sub-tile
+      // in every thread was the top stall of the fused-GELU epilogue); double buffered by tile
+      // parity, ordered by the sub-tile barrier below
+      __nv_bfloat16* bias_s = nullptr;
+      if (p.bias != nullptr && p.grp_mblocks == 0) {
+        bias_s = smem_bias + acc * BLOCK_N;
+        const int t = threadIdx.x - 64;                        // 0 .. 255 over the epilogue warps
+        if (t < BLOCK_N) bias_s[t] = (n0 + t < p.N) ? p.bias[n0 + t] : __float2bfloat16(0.f);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
       const int n_sub = (min(BLOCK_N, p.N - n0) + kStoreCols - 1) / kStoreCols;
-      if (in_tma && issuer) {
-        tma_store_wait_read<0>();
-        mbar_expect_tx(&in_bar[store_buf], kStoreBytes);
-        tma_load_2d(&tmap_in, &in_bar[store_buf], smem_store + store_buf * kStoreBytes, n0, m0);
-      }
+      if (bias_s != nullptr && (NB >= 4)) epi_bar_sync();      // (NB == 2: the first barrier below)
 #pragma unroll 1
-      for (int sub = 0; sub < n_sub; ++sub) {
+      for (int sub = 0; sub < n_sub; ++sub, ++q) {
         const int sc = sub * kStoreCols;
-        uint8_t* sbuf = smem_store + store_buf * kStoreBytes;
-        uint8_t* obuf = smem_store + (store_buf ^ 1) * kStoreBytes;
-        if (issuer) {
-          if (in_tma) {
-            tma_store_wait_read<0>();
-            if (sub + 1 < n_sub) {
-              mbar_expect_tx(&in_bar[store_buf ^ 1], kStoreBytes);
-              tma_load_2d(&tmap_in, &in_bar[store_buf ^ 1], obuf, n0 + sc + kStoreCols, m0);
-            }
-          } else if (aux_tma) {
-            tma_store_wait_read<0>();
-          } else {
-            tma_store_wait_read<1>();
-          }
+        const int b0 = aux_tma ? static_cast<int>(2 * (q % (NB / 2))) : static_cast<int>(q % NB);
+        uint8_t* sbuf = smem_store + b0 * kStoreBytes;
+        uint8_t* obuf = smem_store + (b0 ^ 1) * kStoreBytes;      // second output (aux mode only)
+        if (issuer && in_tma) {
+          tma_store_wait_read<NB - kPrefetch - 1>();
+          pf_issue();                                         // input of sub-tile q + kPrefetch
         }
-        epi_bar_sync();
+        if constexpr (NB < 4) {
+          // two buffers: everybody waits until the issuer has seen the buffer read out
+          if (issuer && !in_tma) {
+            if (aux_tma) tma_store_wait_read<NB / 2 - 1>();
+            else tma_store_wait_read<NB - 1>();
+          }
+          epi_bar_sync();
+        }
+        // (deep ring: the buffer of sub-tile q was confirmed free by the issuer before the closing
+        //  barrier of sub-tile q-1, see below -- one barrier per sub-tile; in input mode the
+        //  buffer's own mbarrier is the hand-over)
         if (in_tma) {
-          mbar_wait(&in_bar[store_buf], (in_phase >> store_buf) & 1u);
-          in_phase ^= (1u << store_buf);
+          mbar_wait(&in_bar[b0], (in_phase >> b0) & 1u);
+          in_phase ^= (1u << b0);
         }
         uint8_t* srow = sbuf + row_in_tile * 128;
         uint8_t* orow = obuf + row_in_tile * 128;
@@ -288,7 +342,8 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           epilogue_load_acc(p, r, v);
           if (row_ok && col0 < p.N)
             epilogue_math(p, v, row, col0, col0 + 32 <= p.N, in_tma ? srow : nullptr,
-                          aux_tma ? srow : nullptr, h, swz);
+                          aux_tma ? srow : nullptr, h, swz,
+                          bias_s != nullptr ? bias_s + sc + h * 32 : nullptr);
           uint8_t* wrow = aux_tma ? orow : srow;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -307,6 +362,14 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
         }
         fence_proxy_async_smem();
+        if constexpr (NB >= 4) {
+          // the buffer (pair) of the NEXT sub-tile must have been read out: NB-2 (NB/2-2) newer
+          // store groups may still be pending at this point (store(q) is committed below)
+          if (issuer && !in_tma) {
+            if (aux_tma) tma_store_wait_read<NB / 2 - 2>();
+            else tma_store_wait_read<NB - 2>();
+          }
+        }
         epi_bar_sync();
         if (issuer) {
           if (aux_tma) {
@@ -317,7 +380,6 @@ gemm_bf16_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           tma_store_commit();
         }
-        if (!aux_tma) store_buf ^= 1;
       }
       if (++acc == 2) {
         acc = 0;

@@ -28,7 +28,8 @@ BUILD_DIR = REPO / "build" / "tdp_b200"
 SO_PATH = PKG_DIR / "_C.so"
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = [
+_EXTRA_DEFS = [f"-D{d}" for d in os.environ.get("TDP_NVCC_DEFS", "").split() if d]
+NVCC_FLAGS = [*_EXTRA_DEFS,
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
