@@ -231,7 +231,17 @@ def grad_check_ours(step, batch, world, device):
     lr0 = float(opt.param_groups[0]["lr"])
     opt.set_lr(0.0)
     tokens, targets = batch[:, :-1], batch[:, 1:]
-    step(tokens, targets)
+    fused = bool(getattr(opt, "fused_comm", False))
+    if fused:
+        # fused reduce-scatter -> AdamW -> all-gather kernels never materialise the averaged
+        # gradient; the same kernels run once (eagerly) with their write-back flag on
+        opt.write_back_grad = True
+        try:
+            ctx["eager_step"](tokens.contiguous(), targets.contiguous())
+        finally:
+            opt.write_back_grad = False
+    else:
+        step(tokens, targets)
     torch.cuda.synchronize()
     got = [b.payload().float().clone() for b in red.buckets]
     orig = red._reduce_bucket
@@ -250,13 +260,23 @@ def grad_check_ours(step, batch, world, device):
         worst_l2 = max(worst_l2, float((g - ref).norm() / ref.norm().clamp_min(1e-20)))
         sym += int(b.symm is not None)
     opt.set_lr(lr0)
+    # replicas must hold bit-identical parameters after all those steps (the fused path
+    # multicasts them; a lost store would show up here)
+    chk = torch.stack([st["flat_p"].view(torch.int16).to(torch.int64).sum() for st in opt.state])
+    hi_, lo_ = chk.clone(), chk.clone()
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    params_identical = bool((hi_ == lo_).all().item())
     t = torch.tensor([worst_max, worst_l2], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"grad_check_rel": float(t[0]), "grad_check_rel_l2": float(t[1]),
+            "params_identical_across_ranks": params_identical, "fused_reduce_optimizer": fused,
             "grad_check_buckets": len(red.buckets), "grad_check_symmetric_buckets": sym,
-            "grad_check_how": "graph-replayed step (direct wgrad -> NVLS all-reduce) vs local "
-                              "grads averaged by NCCL all_reduce, same batch, lr=0; max over "
-                              "buckets and ranks of max|diff|/max|ref| and of the L2 ratio"}
+            "grad_check_how": ("the step's own reduction kernels (direct wgrad -> NVLS reduce; fused "
+                               "optimizer mode: run eagerly with the averaged gradient written "
+                               "back) vs local grads averaged by NCCL all_reduce, same batch, "
+                               "lr=0; max over buckets and ranks of max|diff|/max|ref| and of "
+                               "the L2 ratio")}
 
 
 def exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms_with_comm):

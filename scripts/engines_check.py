@@ -53,21 +53,41 @@ for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
 res["ddp_worst_param"] = worst_name
 check("ddp_grad_vs_nccl_avg", worst, 3e-2)
 
-# BucketAdamW vs torch AdamW (fp32 master) for 3 steps on the averaged grads
-opt = BucketAdamW(ddp, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
-ref32 = copy.deepcopy(ref).float()
-ropt = torch.optim.AdamW(ref32.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
-with torch.no_grad():
-    for p, q in zip(ref32.parameters(), model.parameters()):
-        p.copy_(q.float())
-for it in range(3):
-    opt.zero_grad()
-    ddp(tok[:, :-1], tok[:, 1:]).backward(); ddp.reduce_gradients()
-    for p, q in zip(ref32.parameters(), model.parameters()):
-        p.grad = q.grad.float().clone()
-    opt.step(); ropt.step()
-worst = max(rel(q, p) for p, q in zip(ref32.parameters(), model.parameters()))
-check("bucket_adamw_vs_torch", worst, 2e-2)
+# BucketAdamW vs torch AdamW (fp32 master) for 3 steps on the averaged grads: the fused
+# reduce-scatter -> AdamW -> all-gather mode (default on symmetric buckets; the averaged gradient is
+# written back so the torch reference can use it) and the plain all-reduce + per-bucket AdamW mode
+for fused in (True, False):
+    if fused and (world < 2 or res["ddp_symm_buckets"] != len(ddp.buckets)):
+        continue
+    tdp.fix_rand(0, deterministic_cudnn=False)
+    m2 = build_gpt2("tiny", device=dev)
+    d2 = tdp.NaiveDDP(m2, gradient_as_bucket_view=True, process_group=dp, bucket_cap_mb=0.25)
+    opt = BucketAdamW(d2, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, fused_comm=fused)
+    assert opt.fused_comm == fused
+    opt.write_back_grad = True
+    ref32 = copy.deepcopy(m2).float()
+    ropt = torch.optim.AdamW(ref32.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    with torch.no_grad():
+        for p, q in zip(ref32.parameters(), m2.parameters()):
+            p.copy_(q.float())
+    for it in range(3):
+        opt.zero_grad()
+        d2(tok[:, :-1], tok[:, 1:]).backward(); d2.reduce_gradients()
+        opt.step()
+        torch.cuda.synchronize()
+        for p, q in zip(ref32.parameters(), m2.parameters()):
+            p.grad = q.grad.float().clone()          # averaged gradient (written back if fused)
+        ropt.step()
+    worst = max(rel(q, p) for p, q in zip(ref32.parameters(), m2.parameters()))
+    check("bucket_adamw_fused_vs_torch" if fused else "bucket_adamw_vs_torch", worst, 2e-2)
+    # replicas stay bit-identical
+    chk = torch.stack([st["flat_p"].view(torch.int16).to(torch.int64).sum() for st in opt.state])
+    hi_, lo_ = chk.clone(), chk.clone()
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX); dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    check("replicas_identical_fused" if fused else "replicas_identical", float((hi_ != lo_).sum().item()), 0.5)
+    d2.remove_hooks()
+    del d2, opt, m2
+opt = None
 del ddp, opt
 
 # ---------------------------------------------------------------- ZeRO (bf16 model, fused path)

@@ -16,6 +16,8 @@
 // These replace the reference's NCCL calls: dist.all_reduce on DDP buckets (ddp/naive_ddp.py:104-127),
 // ZeRO's all_reduce + per-tensor broadcast (ddp/zero_optim.py:73-95,282-287), TP/SP collectives
 // (parallel/tensor_parallel/tp_utils.py:44,67,84).
+#include <stdlib.h>
+
 #include "../common/ptx.cuh"
 #include "../common/tdp_api.h"
 
@@ -23,8 +25,22 @@ namespace tdp {
 
 namespace {
 
-constexpr int kCollThreads = 512;
-constexpr int kMaxCollBlocks = 64;          // barrier slots reserved per signal pad region
+// CTA shape of the collective kernels.  Measured on 2 x B200 inside the overlapped GPT-2 step
+// (profiles/r2/ab_n2.txt): 512-thread CTAs (32 of them) beat 128-thread CTAs that co-reside with
+// the persistent GEMM CTAs on every SM (18.94 vs 19.42 ms/step fused, 19.23 vs 19.46 plain) --
+// fewer, fatter CTAs disturb fewer GEMM CTAs.  TDP_COLL_THREADS = 128 | 256 | 512 overrides.
+constexpr int kCollThreadsMax = 512;        // __launch_bounds__ of the collective kernels
+constexpr int kMaxCollBlocks = 128;         // barrier slots reserved per signal pad region
+// CTA shape actually launched: TDP_COLL_THREADS (128 | 256 | 512), default 512
+inline int coll_threads() {
+  static const int v = [] {
+    const char* e = getenv("TDP_COLL_THREADS");
+    const int t = e ? atoi(e) : 512;
+    return (t == 128 || t == 256) ? t : 512;
+  }();
+  return v;
+}
+#define kCollThreads coll_threads()
 constexpr int kBarrierSlotWords = kMaxCollBlocks * kApiMaxPeers;   // words per barrier "slot"
 
 struct PeerPtrs {
@@ -138,7 +154,7 @@ __device__ __forceinline__ uint4 reduce16(const PeerPtrs& pp, const char* mc, in
 // all-reduce (two-shot, in place)
 // ------------------------------------------------------------------------------------------
 template <bool kMc, bool kFp32>
-__global__ void __launch_bounds__(kCollThreads)
+__global__ void __launch_bounds__(kCollThreadsMax)
 all_reduce_two_shot_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset,
                            size_t n_vec /*16-byte vectors*/, float scale, int slot_base) {
   block_barrier(pp, rank, world, slot_base);
@@ -176,10 +192,96 @@ all_reduce_two_shot_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int ra
 }
 
 // ------------------------------------------------------------------------------------------
+// reduce-scatter -> AdamW on my shard -> all-gather of the updated bf16 parameters, ONE kernel.
+// The data-parallel step of a bucket is the two shots of the all-reduce with the optimizer in
+// between: rank r reduces slice r of the gradient bucket in the switch, updates the fp32 master
+// weights / moments of exactly that slice (optimizer state and traffic are 1/N per rank), and
+// multicasts the new bf16 parameters into every rank's parameter buffer.  Same NVLink bytes as a
+// plain all-reduce, no separate optimizer pass over all parameters, no post-backward tail.
+// (reference: ddp/naive_ddp.py:104-127 all-reduce + a full torch optimizer step on every rank)
+// ------------------------------------------------------------------------------------------
+struct AdamC {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;
+  int adamw;
+};
+__device__ __forceinline__ float adam_step(float p, float g, float& m, float& v, const AdamC& c) {
+  if (!c.adamw) g += c.wd * p;
+  else p *= (1.f - c.lr * c.wd);
+  m = c.beta1 * m + (1.f - c.beta1) * g;
+  v = c.beta2 * v + (1.f - c.beta2) * g * g;
+  const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+  return p - (c.lr / c.bc1) * (m / denom);
+}
+
+template <bool kMc, bool kWriteGrad>
+__global__ void __launch_bounds__(kCollThreadsMax)
+fused_rs_adamw_ag_kernel(const __grid_constant__ PeerPtrs gp, char* gmc,
+                         const __grid_constant__ PeerPtrs pp, char* pmc, int rank, int world,
+                         FusedAdamLaunch a, int slot_base) {
+  AdamC c;
+  {
+    const float step = a.hyper[0];
+    c.lr = a.hyper[1];
+    c.beta1 = a.beta1; c.beta2 = a.beta2; c.eps = a.eps; c.wd = a.weight_decay;
+    c.bc1 = 1.f - powf(a.beta1, step);
+    c.bc2_sqrt = sqrtf(1.f - powf(a.beta2, step));
+    c.adamw = a.adamw_mode;
+  }
+  block_barrier(gp, rank, world, slot_base);          // every rank's gradients of this bucket are final
+  const size_t per = (a.n_vec + world - 1) / world;
+  const size_t lo = min(per * rank, a.n_vec), hi = min(lo + per, a.n_vec);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  constexpr int kUnroll = 4;
+  for (size_t i = lo + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hi;
+       i += stride * kUnroll) {
+    uint4 g[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx < hi) g[u] = reduce16<kMc, false>(gp, gmc, world, a.grad_offset + idx * 16, a.grad_scale);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t idx = i + u * stride;
+      if (idx >= hi) continue;
+      const size_t li = (idx - lo) * 2;                 // float4 index inside my shard
+      float4* mp = reinterpret_cast<float4*>(a.master) + li;
+      float4* m1 = reinterpret_cast<float4*>(a.exp_avg) + li;
+      float4* m2 = reinterpret_cast<float4*>(a.exp_avg_sq) + li;
+      float4 p0 = mp[0], p1 = mp[1], e0 = m1[0], e1 = m1[1], s0 = m2[0], s1 = m2[1];
+      const float2 ga = unpack_bf16x2(g[u].x), gb = unpack_bf16x2(g[u].y),
+                   gc = unpack_bf16x2(g[u].z), gd = unpack_bf16x2(g[u].w);
+      p0.x = adam_step(p0.x, ga.x, e0.x, s0.x, c); p0.y = adam_step(p0.y, ga.y, e0.y, s0.y, c);
+      p0.z = adam_step(p0.z, gb.x, e0.z, s0.z, c); p0.w = adam_step(p0.w, gb.y, e0.w, s0.w, c);
+      p1.x = adam_step(p1.x, gc.x, e1.x, s1.x, c); p1.y = adam_step(p1.y, gc.y, e1.y, s1.y, c);
+      p1.z = adam_step(p1.z, gd.x, e1.z, s1.z, c); p1.w = adam_step(p1.w, gd.y, e1.w, s1.w, c);
+      mp[0] = p0; mp[1] = p1; m1[0] = e0; m1[1] = e1; m2[0] = s0; m2[1] = s1;
+      uint4 o;
+      o.x = pack_bf16x2(p0.x, p0.y); o.y = pack_bf16x2(p0.z, p0.w);
+      o.z = pack_bf16x2(p1.x, p1.y); o.w = pack_bf16x2(p1.z, p1.w);
+      const size_t poff = a.param_offset + idx * 16;
+      const size_t goff = a.grad_offset + idx * 16;
+      if constexpr (kMc) {
+        multimem_st_v4(pmc + poff, o);
+        if constexpr (kWriteGrad) multimem_st_v4(gmc + goff, g[u]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kApiMaxPeers; ++q)
+          if (q < world) {
+            st_na_v4(reinterpret_cast<char*>(pp.buf[q]) + poff, o);
+            if constexpr (kWriteGrad) st_na_v4(reinterpret_cast<char*>(gp.buf[q]) + goff, g[u]);
+          }
+      }
+    }
+  }
+  block_barrier(gp, rank, world, slot_base + kBarrierSlotWords);   // new parameters visible everywhere
+}
+
+// ------------------------------------------------------------------------------------------
 // reduce-scatter: slice `rank` of [world x slice] -> out (local)
 // ------------------------------------------------------------------------------------------
 template <bool kMc, bool kFp32In>
-__global__ void __launch_bounds__(kCollThreads)
+__global__ void __launch_bounds__(kCollThreadsMax)
 reduce_scatter_kernel(const __grid_constant__ PeerPtrs pp, const char* mc, int rank, int world, size_t offset,
                       size_t slice_vec, float scale, void* out, int out_fp32, int accumulate,
                       int slot_base) {
@@ -235,7 +337,7 @@ reduce_scatter_kernel(const __grid_constant__ PeerPtrs pp, const char* mc, int r
 // all-gather: my slice (local src) -> slot `rank` of the symmetric region on every rank
 // ------------------------------------------------------------------------------------------
 template <bool kMc>
-__global__ void __launch_bounds__(kCollThreads)
+__global__ void __launch_bounds__(kCollThreadsMax)
 all_gather_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, size_t offset, size_t slice_vec,
                   const uint4* src, int slot_base, uint32_t* flag_base_unused) {
   block_barrier(pp, rank, world, slot_base);
@@ -321,7 +423,7 @@ all_gather_signal_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank
 // second stage of fused GEMM->reduce-scatter / GEMM->all-reduce
 // ------------------------------------------------------------------------------------------
 template <bool kMc>
-__global__ void __launch_bounds__(kCollThreads)
+__global__ void __launch_bounds__(kCollThreadsMax)
 rs_reduce_kernel(const __grid_constant__ PeerPtrs pp, char* mc, int rank, int world, RsReduceLaunch r) {
   // wait until every source rank has delivered all of its tiles for my chunk
   if (threadIdx.x < world) {
@@ -440,8 +542,9 @@ PeerPtrs to_pp(const SymmPeers& s) {
 }
 
 int pick_blocks(size_t n_vec_per_rank, int max_ctas) {
-  size_t want = (n_vec_per_rank + kCollThreads * 4 - 1) / (kCollThreads * 4);
-  int cap = max_ctas > 0 ? max_ctas : 32;
+  size_t want = (n_vec_per_rank + kCollThreads * 8 - 1) / (kCollThreads * 8);
+  // default cap keeps ~16 K threads in flight whatever the CTA shape
+  int cap = max_ctas > 0 ? max_ctas : (16384 / kCollThreads);
   if (cap > kMaxCollBlocks) cap = kMaxCollBlocks;
   if (want < 1) want = 1;
   return static_cast<int>(want < static_cast<size_t>(cap) ? want : cap);
@@ -494,6 +597,23 @@ void launch_all_reduce(const SymmPeers& s, size_t offset, size_t numel, int dtyp
   }
 }
 
+void launch_fused_rs_adamw_ag(const SymmPeers& grad, const SymmPeers& param,
+                              const FusedAdamLaunch& a, int use_mc, int write_back_grad,
+                              int max_ctas, cudaStream_t stream) {
+  const bool mc = use_mc && grad.mc_buf != nullptr && param.mc_buf != nullptr;
+  const int world = grad.world > 0 ? grad.world : 1;
+  const int blocks = pick_blocks(a.n_vec / world / 2 + 1, max_ctas);
+  PeerPtrs gp = to_pp(grad), pp = to_pp(param);
+  char* gmc = reinterpret_cast<char*>(grad.mc_buf);
+  char* pmc = reinterpret_cast<char*>(param.mc_buf);
+#define TDP_FUSED(MC, WG)                                                                  \
+  fused_rs_adamw_ag_kernel<MC, WG><<<blocks, kCollThreads, 0, stream>>>(gp, gmc, pp, pmc,   \
+                                                                         grad.rank, world, a, 0)
+  if (mc) { if (write_back_grad) TDP_FUSED(true, true); else TDP_FUSED(true, false); }
+  else    { if (write_back_grad) TDP_FUSED(false, true); else TDP_FUSED(false, false); }
+#undef TDP_FUSED
+}
+
 void launch_reduce_scatter(const SymmPeers& s, size_t offset, size_t slice_numel, int dtype,
                            float scale, void* out, int out_fp32, int accumulate_out, int use_mc,
                            int max_ctas, cudaStream_t stream) {
@@ -533,8 +653,7 @@ void launch_all_gather_signal(const SymmPeers& s, size_t offset, size_t slice_by
                               int use_mc, int max_ctas, cudaStream_t stream) {
   const size_t slice_vec = slice_bytes / 16;
   const bool mc = use_mc && s.mc_buf != nullptr;
-  // max_ctas is given in units of kCollThreads-wide CTAs; the push CTAs are half as wide
-  const int blocks = pick_blocks(slice_vec, max_ctas * (kCollThreads / kPushThreads));
+  const int blocks = pick_blocks(slice_vec, max_ctas);
   PeerPtrs pp = to_pp(s);
   char* mcp = reinterpret_cast<char*>(s.mc_buf);
   uint32_t* ticket = ticket_counter();
@@ -552,7 +671,7 @@ void launch_rs_reduce(const SymmPeers& s, const RsReduceLaunch& r, int use_mc, i
                       cudaStream_t stream) {
   const bool mc = use_mc && s.mc_buf != nullptr;
   const size_t total_vec = static_cast<size_t>(r.rows) * (r.cols / 8);
-  int blocks = pick_blocks(total_vec, max_ctas > 0 ? max_ctas : 64);
+  int blocks = pick_blocks(total_vec, max_ctas > 0 ? max_ctas : kMaxCollBlocks);
   PeerPtrs pp = to_pp(s);
   char* mcp = reinterpret_cast<char*>(s.mc_buf);
   if (mc) rs_reduce_kernel<true><<<blocks, kCollThreads, 0, stream>>>(pp, mcp, s.rank, s.world, r);

@@ -79,6 +79,23 @@ void launch_all_reduce(const SymmPeers& s, size_t offset, size_t numel, int dtyp
 
 // reduce-scatter: rank r ends up with the reduced slice r of [world * slice_numel] at `offset`
 // written to `out` (bf16/fp32 selectable; out_fp32 accumulates into fp32 master grads).
+// reduce-scatter -> AdamW on this rank's 1/N shard -> all-gather of the new bf16 parameters in ONE
+// kernel (collectives.cu).  `grad` / `param`: symmetric buffers of the same group; offsets in
+// bytes; n_vec = 16-byte vectors (8 bf16) in the bucket payload; master / exp_avg / exp_avg_sq: this
+// rank's fp32 shard, ceil(n_vec / world) * 8 floats each; hyper: device floats {step, lr}.
+struct FusedAdamLaunch {
+  size_t grad_offset, param_offset, n_vec;
+  float* master;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float beta1, beta2, eps, weight_decay;
+  int adamw_mode;
+  const float* hyper;
+  float grad_scale;
+};
+void launch_fused_rs_adamw_ag(const SymmPeers& grad, const SymmPeers& param,
+                              const FusedAdamLaunch& a, int use_mc, int write_back_grad,
+                              int max_ctas, cudaStream_t stream);
 void launch_reduce_scatter(const SymmPeers& s, size_t offset, size_t slice_numel, int dtype,
                            float scale, void* out, int out_fp32, int accumulate_out, int use_mc,
                            int max_ctas, cudaStream_t stream);

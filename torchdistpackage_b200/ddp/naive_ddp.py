@@ -58,6 +58,9 @@ class GradBucket:
         self._ready = 0
         self.pending_work = None
         self.reduced = False
+        # set by BucketAdamW(fused_comm=True): replaces the all-reduce of this bucket with the
+        # fused reduce-scatter -> AdamW -> all-gather kernel
+        self.fused_step = None
 
     # ---- layout
     def elem_align(self) -> int:
@@ -301,7 +304,9 @@ class _GradReducer:
             with torch.cuda.stream(self.comm_stream):
                 self._pack(bucket)
                 payload = bucket.payload()
-                if bucket.symm is not None:
+                if bucket.symm is not None and bucket.fused_step is not None:
+                    bucket.fused_step(bucket)
+                elif bucket.symm is not None:
                     sbuf, off = bucket.symm
                     sbuf.all_reduce_(off, payload.numel(), bucket.dtype,
                                      (1.0 / world) if self.average else 1.0)

@@ -90,13 +90,15 @@ class GPT2Block(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, T, D = x.shape
-        h = F_ops.layer_norm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
+        # layer_norm_fork: LN(x) plus an alias of x for the skip connection, so the two gradients
+        # of x are summed inside the LayerNorm backward kernel (no separate add kernels)
+        h, skip = F_ops.layer_norm_fork(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
         qkv = L_ops.linear(h, self.w_qkv, self.b_qkv, layout="kn")
         o = packed_attention(qkv, self.n_head, causal=True)                # [B, T, D], no layout copies
-        x = L_ops.linear(o, self.w_proj, self.b_proj, layout="kn", residual=x)   # x + proj(o)
-        h = F_ops.layer_norm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
+        x = L_ops.linear(o, self.w_proj, self.b_proj, layout="kn", residual=skip)  # x + proj(o)
+        h, skip = F_ops.layer_norm_fork(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
         return L_ops.mlp(h, self.w_fc1, self.b_fc1, self.w_fc2, self.b_fc2, layout="kn",
-                         act="gelu_tanh", residual=x)                      # x + mlp(h)
+                         act="gelu_tanh", residual=skip)                   # x + mlp(h)
 
 
 class GPT2(nn.Module):

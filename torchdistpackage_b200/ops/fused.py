@@ -16,6 +16,11 @@ import torch.nn.functional as F
 from ._loader import native
 
 
+def dist_rank(group=None) -> int:
+    import torch.distributed as dist
+    return dist.get_rank(group) if dist.is_initialized() else 0
+
+
 def _fused_ok(*ts) -> bool:
     if native() is None:
         return False
@@ -53,6 +58,54 @@ class _LayerNormFn(torch.autograd.Function):
         native().layernorm_bwd(dy2, xin, weight, mean, rstd, dx, ds2, dgamma, dbeta)
         dxv = dx.view(ctx.shape)
         return dxv, dgamma, (dbeta if ctx.has_bias else None), None, (dxv if ctx.has_res else None)
+
+
+class _LayerNormForkFn(torch.autograd.Function):
+    """``(LN(x), x)``: the pre-LN residual fork of a transformer block as ONE autograd node.
+
+    ``x`` feeds both the LayerNorm and the residual add further down; autograd would sum the two
+    gradient contributions with a separate element-wise kernel (24 of them per GPT-2-small step).
+    Here the second output is ``x`` itself (an alias), and backward hands both incoming gradients
+    to the LayerNorm backward kernel, which adds the skip gradient while it writes ``dx``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        rows, cols = x2.shape
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        native().layernorm_fwd(x2, None, weight, bias, y, None, mean, rstd, float(eps))
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.shape = shape
+        return y.view(shape), x.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        xin, weight, mean, rstd = ctx.saved_tensors
+        rows, cols = xin.shape
+        if dy is None:                       # only the skip path was used
+            return dskip, None, None, None
+        dy2 = dy.reshape(rows, cols).contiguous()
+        ds2 = dskip.reshape(rows, cols).contiguous() if dskip is not None else None
+        dx = torch.empty_like(xin)
+        dgamma = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        dbeta = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        native().layernorm_bwd(dy2, xin, weight, mean, rstd, dx, ds2, dgamma, dbeta)
+        return dx.view(ctx.shape), dgamma, (dbeta if ctx.has_bias else None), None
+
+
+def layer_norm_fork(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                    eps: float = 1e-5):
+    """``h, skip = layer_norm_fork(x, w, b)``: ``h = LN(x)`` and ``skip`` is ``x`` for the residual
+    connection; use ``skip`` (not ``x``) downstream so that the two gradients meet inside the
+    LayerNorm backward kernel instead of in a separate add."""
+    cols = x.shape[-1]
+    if _fused_ok(x, weight, bias, None) and cols % 8 == 0 and cols <= 8192 and x.is_contiguous():
+        return _LayerNormForkFn.apply(x, weight, bias, eps)
+    return F.layer_norm(x, (cols,), weight, bias, eps), x
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
@@ -242,7 +295,18 @@ class BucketAdamW:
     """
 
     def __init__(self, ddp, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-                 master_weights: bool = True, adamw_mode: bool = True):
+                 master_weights: bool = True, adamw_mode: bool = True,
+                 fused_comm: Optional[bool] = None):
+        """``fused_comm`` (default: on whenever the DDP buckets live in NVSwitch symmetric memory,
+        ``TDP_FUSED_OPT=0`` turns it off): the data-parallel reduction and the optimizer become ONE
+        kernel per bucket -- reduce-scatter in the switch, AdamW on this rank's 1/N shard of the
+        fp32 master weights / moments, multicast all-gather of the new bf16 parameters
+        (csrc/coll/collectives.cu ``fused_rs_adamw_ag_kernel``).  It runs on the DDP comm stream as
+        soon as a bucket's gradients are complete, i.e. overlapped with the rest of backward;
+        optimizer state and optimizer memory traffic shrink to 1/N per rank and ``step()`` has
+        nothing left to do.  In this mode ``p.grad`` keeps the *local* gradient after the step
+        (set ``write_back_grad = True`` to also publish the averaged one, e.g. for checks) and
+        ``grad_scale`` / clipping between reduction and update is not available."""
         red = ddp.reducer
         if not red.as_view:
             raise ValueError("BucketAdamW needs NaiveDDP(gradient_as_bucket_view=True)")
@@ -259,9 +323,33 @@ class BucketAdamW:
         if red.on_cuda:
             self._hyper = torch.tensor([0.0, float(lr)], dtype=torch.float32, device=red.device)
             self._hyper_lr = float(lr)
+        import os
+        world = red._group_size(red.default_group)
+        can_fuse = (red.on_cuda and native() is not None and world > 1 and master_weights
+                    and len(red.buckets) > 0
+                    and all(b.symm is not None and b.dtype == torch.bfloat16
+                            and red._group_size(b.group) == world for b in red.buckets))
+        if fused_comm is None:
+            fused_comm = can_fuse and os.environ.get("TDP_FUSED_OPT", "1") != "0"
+        elif fused_comm and not can_fuse:
+            raise ValueError("BucketAdamW(fused_comm=True) needs bf16 NaiveDDP buckets in symmetric "
+                             "memory (NCCL group of 2..8 GPUs on one NVSwitch domain)")
+        self.fused_comm = bool(fused_comm)
+        self.write_back_grad = False
+        self._step_open = False
+        self._world = world
+        param_sbufs = {}
         with torch.no_grad():
             for b in red.buckets:
-                flat_p = torch.zeros(b.capacity, dtype=b.dtype, device=b.device)
+                if self.fused_comm:
+                    # parameters mirror the gradient layout inside a second symmetric buffer
+                    gsbuf, goff = b.symm
+                    if id(gsbuf) not in param_sbufs:
+                        param_sbufs[id(gsbuf)] = gsbuf.group.alloc(gsbuf.nbytes)
+                    psbuf = param_sbufs[id(gsbuf)]
+                    flat_p = psbuf.view(goff, (b.capacity,), b.dtype)
+                else:
+                    flat_p = torch.zeros(b.capacity, dtype=b.dtype, device=b.device)
                 esize = b.buffer.element_size()
                 for name in b.names:
                     p = red.params[name]
@@ -269,12 +357,45 @@ class BucketAdamW:
                     pv = flat_p[off:off + p.numel()].view(p.shape)
                     pv.copy_(p.data)
                     p.data = pv
-                st = dict(bucket=b, flat_p=flat_p,
-                          exp_avg=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
-                          exp_avg_sq=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
-                          master=(flat_p.float().clone() if master_weights and
-                                  b.dtype != torch.float32 else None))
+                if self.fused_comm:
+                    n = b.payload().numel()                       # multiple of 256 elements
+                    n_vec = n // 8
+                    per = (n_vec + world - 1) // world            # 16-byte vectors per rank
+                    rank = dist_rank(red.default_group)
+                    lo, hi = min(per * rank, n_vec) * 8, min(per * (rank + 1), n_vec) * 8
+                    master = torch.zeros(per * 8, dtype=torch.float32, device=b.device)
+                    master[:hi - lo].copy_(flat_p[lo:hi])
+                    st = dict(bucket=b, flat_p=flat_p, master=master, numel=n, lo=lo, hi=hi,
+                              exp_avg=torch.zeros_like(master), exp_avg_sq=torch.zeros_like(master),
+                              param_sbuf=psbuf, off=goff)
+                    b.fused_step = self._make_fused_step(st)
+                else:
+                    st = dict(bucket=b, flat_p=flat_p,
+                              exp_avg=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
+                              exp_avg_sq=torch.zeros(b.capacity, dtype=torch.float32, device=b.device),
+                              master=(flat_p.float().clone() if master_weights and
+                                      b.dtype != torch.float32 else None))
                 self.state.append(st)
+        if self.fused_comm:
+            for psbuf in param_sbufs.values():
+                psbuf.barrier(0)      # every rank's parameters are in place before anyone multicasts
+
+    def _make_fused_step(self, st):
+        def run(bucket):
+            """Called by the DDP reducer on its comm stream when the bucket's gradients are final."""
+            g = self.param_groups[0]
+            if not self._step_open:
+                self._hyper[0:1].add_(1.0)            # one optimizer step per backward pass
+                self._step_open = True
+            gsbuf, goff = bucket.symm
+            b1, b2 = g["betas"]
+            gsbuf.handle.fused_rs_adamw_ag(
+                st["param_sbuf"].handle, goff, st["off"], st["numel"], st["master"], st["exp_avg"],
+                st["exp_avg_sq"], float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                bool(self.adamw_mode), self._hyper,
+                (1.0 / self._world) if self.ddp.reducer.average else 1.0,
+                bool(self.write_back_grad), 0)
+        return run
 
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0, grad_scale_t: Optional[torch.Tensor] = None):
@@ -282,6 +403,19 @@ class BucketAdamW:
         b1, b2 = g["betas"]
         self.step_count += 1
         C = native()
+        if self.fused_comm:
+            # the update already happened, bucket by bucket, inside the reduction kernels that
+            # NaiveDDP launched during backward / reduce_gradients()
+            if grad_scale != 1.0 or grad_scale_t is not None:
+                raise ValueError("BucketAdamW(fused_comm=True): no grad_scale / clipping hook "
+                                 "between reduction and update; build it with fused_comm=False")
+            if not self.ddp.reducer._finalized:
+                self.ddp.reducer.finalize()
+            if not torch.cuda.is_current_stream_capturing() and g["lr"] != self._hyper_lr:
+                self._hyper[1].fill_(float(g["lr"]))
+                self._hyper_lr = float(g["lr"])
+            self._step_open = False
+            return
         if self._hyper is not None:
             if not torch.cuda.is_current_stream_capturing() and g["lr"] != self._hyper_lr:
                 self._hyper[1].fill_(float(g["lr"]))      # LR schedulers edit param_groups
@@ -339,13 +473,17 @@ class BucketAdamW:
 
     def state_dict(self) -> dict:
         self.step_count = self.current_step()      # replays advance only the device counter
-        return dict(step=self.step_count, param_groups=[{k: v for k, v in g.items() if k != "params"}
+        return dict(step=self.step_count, fused_comm=self.fused_comm, world=self._world, param_groups=[{k: v for k, v in g.items() if k != "params"}
                                                         for g in self.param_groups],
                     buckets=[dict(exp_avg=s["exp_avg"].cpu(), exp_avg_sq=s["exp_avg_sq"].cpu(),
                                   master=None if s["master"] is None else s["master"].cpu())
                              for s in self.state])
 
     def load_state_dict(self, sd: dict) -> None:
+        if bool(sd.get("fused_comm", False)) != self.fused_comm or \
+                (self.fused_comm and int(sd.get("world", self._world)) != self._world):
+            raise ValueError("BucketAdamW checkpoint was written with a different fused_comm / "
+                             "world size (optimizer shards are rank-local in fused mode)")
         self.step_count = int(sd["step"])
         for g, sg in zip(self.param_groups, sd["param_groups"]):
             g.update(sg)
@@ -358,7 +496,12 @@ class BucketAdamW:
             s["exp_avg_sq"].copy_(ss["exp_avg_sq"])
             if s["master"] is not None and ss["master"] is not None:
                 s["master"].copy_(ss["master"])
-                s["flat_p"].copy_(s["master"])
+                if self.fused_comm:
+                    # my slice of the bf16 parameters; the other slices come from the model
+                    # checkpoint (identical on every rank)
+                    s["flat_p"][s["lo"]:s["hi"]].copy_(s["master"][:s["hi"] - s["lo"]])
+                else:
+                    s["flat_p"].copy_(s["master"])
 
 
 def flatten_module_params(module: torch.nn.Module, align_elems: int = 64):

@@ -20,7 +20,7 @@ import torch.distributed as dist
 from ._loader import native
 
 SIGNAL_PAD_BYTES = 64 * 1024
-USER_WORD_BASE = 2048
+USER_WORD_BASE = 4096        # first word after the barrier slots (3 x 128 blocks x 8 peers)
 _MAX_WORLD = 8
 
 
