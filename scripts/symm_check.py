@@ -47,7 +47,10 @@ ok = True
 for dtype in (torch.bfloat16, torch.float32):
     for n in (1024, 1 << 20, (13 << 20) + 8):
         x = torch.randn(n, device=dev).to(dtype)
-        for algo in ((3, 2) if buf.has_multicast else (2,)):
+        algos = (3, 2) if buf.has_multicast else (2,)
+        if n * x.element_size() <= 256 * 1024:           # one-shot latency path (NVLS / P2P loads)
+            algos = algos + ((4, 1) if buf.has_multicast else (1,))
+        for algo in algos:
             v = buf.view(0, (n,), dtype)
             v.copy_(x)
             buf.all_reduce_(0, n, dtype, 1.0 / world, algo=algo)
@@ -99,6 +102,19 @@ for mb in (1, 8, 25, 64, 256):
             rec[k.replace("_ms", "_busbw")] = mb * (1 << 20) / (rec[k] * 1e-3) * 2 * (world - 1) / world / 1e9
     bw.append(rec); log(rec)
 res["allreduce_bw"] = bw
+
+# ------------------------------------------------------------------ small-message latency vs NCCL
+lat = []
+for kib in (2, 16, 64, 256):
+    n = kib * 1024 // 2
+    t = torch.randn(n, device=dev).to(torch.bfloat16)
+    rec = {"KiB": kib, "nccl_us": timeit(lambda: dist.all_reduce(t)) * 1e3}
+    for name, algo in (("one_shot_nvls", 4), ("one_shot_p2p", 1), ("two_shot_nvls", 3)):
+        if algo in (3, 4) and not buf.has_multicast:
+            continue
+        rec[name + "_us"] = timeit(lambda: buf.all_reduce_(0, n, torch.bfloat16, 1.0, algo=algo)) * 1e3
+    lat.append(rec); log(rec)
+res["allreduce_latency"] = lat
 
 # ------------------------------------------------------------------ fused GEMM -> reduce-scatter
 T, Kl, N = 2048 * world if world <= 4 else 8192, 2048, 4096

@@ -73,9 +73,12 @@ void launch_symm_barrier(const SymmPeers& s, int slot, cudaStream_t stream);
 
 // in-place all-reduce of `numel` elements at byte offset `offset` of the symmetric buffer.
 // dtype: 0 = bf16, 1 = fp32.  scale is applied to the sum (1/N for AVG).
-// algo: 0 = auto, 1 = one-shot p2p, 2 = two-shot p2p, 3 = NVLS multimem two-shot
+// algo: 0 = auto, 1 = one-shot p2p, 2 = two-shot p2p, 3 = NVLS multimem two-shot, 4 = one-shot NVLS.
+// one_shot_scratch: kOneShotScratchBytes of device memory private to this symmetric buffer (the
+// one-shot latency path for messages up to that size; nullptr disables it).
+constexpr size_t kOneShotScratchBytes = 256 * 1024;
 void launch_all_reduce(const SymmPeers& s, size_t offset, size_t numel, int dtype, float scale,
-                       int algo, int max_ctas, cudaStream_t stream);
+                       int algo, int max_ctas, cudaStream_t stream, void* one_shot_scratch = nullptr);
 
 // reduce-scatter: rank r ends up with the reduced slice r of [world * slice_numel] at `offset`
 // written to `out` (bf16/fp32 selectable; out_fp32 accumulates into fp32 master grads).

@@ -317,6 +317,35 @@ def test_comm(verbose: bool = True) -> bool:
             dist.recv(t, ctx.get_prev_global_rank("pipe"))
             assert float(t[0]) == float(ctx.get_prev_global_rank("pipe"))
         log("passed: p2p(pipe)")
+    # the package's own NVSwitch data plane: symmetric-memory all-reduce (NVLS multimem kernels or
+    # their P2P variant) on every group that lives inside one NVLink domain
+    if dev.type == "cuda":
+        from ..ops._loader import native
+        from ..ops.symm import get_symm_group
+        if native() is not None:
+            seen = set()
+            for mode in ("data", "tensor", "moe_ep", "moe_dp", "node"):
+                if not ctx.is_mode_inited(mode) or ctx.get_group_size(mode) < 2:
+                    continue
+                grp = ctx.get_group(mode)
+                if id(grp) in seen:
+                    continue
+                seen.add(id(grp))
+                sg = get_symm_group(grp)
+                if not sg.enabled:
+                    log(f"skipped: symmetric all_reduce({mode}): {sg.reason}")
+                    continue
+                buf = sg.alloc(1 << 20)
+                ranks = ctx.get_ranks_in_group(mode)
+                for n in (1024, 1 << 18):               # one-shot (latency) and two-shot paths
+                    v = buf.view(0, (n,), torch.bfloat16)
+                    v.fill_(float(rank % 7))
+                    buf.all_reduce_(0, n, torch.bfloat16, 1.0)
+                    torch.cuda.synchronize()
+                    want = float(sum(r % 7 for r in ranks))
+                    assert torch.all(v.float() == want), (mode, n, float(v[0]), want)
+                log(f"passed: symmetric all_reduce({mode}) "
+                    f"[{'NVLS multimem' if buf.has_multicast else 'P2P'}]")
     dist.barrier()
     log("Finished test_comm")
     return True

@@ -121,12 +121,46 @@ def split_tensor_into_1d_equal_chunks(t: torch.Tensor) -> torch.Tensor:
     return flat[r * k:(r + 1) * k]
 
 
+_SG_BUF = {}          # (group id, bytes) -> [SymmBuffer, use counter]: scatter-gather staging
+
+
+def _symm_gather(chunk: torch.Tensor):
+    """All-gather of a pipeline activation chunk over the tensor group on the package's own
+    multicast kernel (one ``multimem.st`` fans out to every TP rank): two ping-pong halves of a
+    symmetric buffer, the kernel's own barriers order the exchange.  Returns ``None`` when the
+    group has no symmetric memory (cross-node TP, gloo, dtype)."""
+    if chunk.dtype not in (torch.bfloat16, torch.float32) or (chunk.numel() * chunk.element_size()) % 16:
+        return None
+    from ...ops._loader import native
+    from ...ops.symm import get_symm_group
+    if native() is None:
+        return None
+    grp = tpc.get_group("tensor")
+    sg = get_symm_group(grp)
+    if not sg.enabled:
+        return None
+    tp = _tp_size()
+    nb = chunk.numel() * chunk.element_size()
+    key = (id(grp), nb)
+    ent = _SG_BUF.get(key)
+    if ent is None:
+        ent = _SG_BUF[key] = [sg.alloc(2 * nb * tp), 0]
+    buf, use = ent[0], ent[1] & 1
+    ent[1] += 1
+    off = use * nb * tp
+    buf.all_gather(off, nb, chunk.contiguous().view(-1))
+    return buf.view(off, (chunk.numel() * tp,), chunk.dtype).clone()
+
+
 def gather_split_1d_tensor(chunk: torch.Tensor) -> torch.Tensor:
     tp = _tp_size()
     if tp == 1:
         return chunk
     out = torch.empty(chunk.numel() * tp, dtype=chunk.dtype, device=chunk.device)
     if chunk.is_cuda:
+        got = _symm_gather(chunk)
+        if got is not None:
+            return got
         dist.all_gather_into_tensor(out, chunk.contiguous(), group=tpc.get_group("tensor"))
     else:
         parts = [torch.empty_like(chunk) for _ in range(tp)]
