@@ -600,8 +600,11 @@ void launch_all_reduce(const SymmPeers& s, size_t offset, size_t numel, int dtyp
   const size_t n_vec = numel * elem / 16;
   // algo 0 (auto): one-shot up to 256 KiB, two-shot above; 1 forces one-shot (P2P loads),
   // 4 one-shot on multimem, 2 / 3 two-shot P2P / NVLS
-  const bool one_shot = one_shot_scratch != nullptr && n_vec * 16 <= kOneShotScratchBytes &&
-                        (algo == 1 || algo == 4 || algo == 0);
+  // (measured on 2 x B200, scripts/symm_check.py: 15.8 us vs 17.8 us two-shot vs 20.8 us NCCL at
+  //  2 KiB; break-even near 32 KiB -- the auto path switches there, explicit algos go to 256 KiB)
+  const bool one_shot = one_shot_scratch != nullptr &&
+                        ((algo == 0 && n_vec * 16 <= 32 * 1024) ||
+                         ((algo == 1 || algo == 4) && n_vec * 16 <= kOneShotScratchBytes));
   if (one_shot) {
     const bool mc1 = algo == 4 || (algo == 0 && s.mc_buf != nullptr);
     const int threads = 256;

@@ -393,12 +393,14 @@ colsum_atomic_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, in
 
 // out[c] = sum_p partial[p][c]: block = 8 warps x 32 columns; warp w sums partials w, w+8, ...
 // (coalesced 128-byte rows), then the 8 warp sums meet in shared memory.
-__global__ void __launch_bounds__(256)
+constexpr int kPrWarps = 32;     // 1024 threads: the kernel is a handful of CTAs deep, so the
+                                 // loads in flight per CTA are what bounds it (was 8 warps: 21 us)
+__global__ void __launch_bounds__(32 * kPrWarps)
 colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, int cols,
                              void* __restrict__ out, int out_bf16, size_t partial_stride_y,
                              void* __restrict__ out_y1) {
   // blockIdx.y selects an independent problem (LayerNorm: 0 = dgamma, 1 = dbeta)
-  __shared__ float sred[8][32];
+  __shared__ float sred[kPrWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + lane;
   partial += blockIdx.y * partial_stride_y;
@@ -406,14 +408,14 @@ colsum_partial_reduce_kernel(const float* __restrict__ partial, int n_partial, i
   float acc = 0.f;
   if (c < cols) {
 #pragma unroll 4
-    for (int p = w; p < n_partial; p += 8) acc += partial[static_cast<size_t>(p) * cols + c];
+    for (int p = w; p < n_partial; p += kPrWarps) acc += partial[static_cast<size_t>(p) * cols + c];
   }
   sred[w][lane] = acc;
   __syncthreads();
   if (w == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sred[i][lane];
+    for (int i = 0; i < kPrWarps; ++i) t += sred[i][lane];
     if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[c] = __float2bfloat16_rn(t);
     else reinterpret_cast<float*>(out)[c] = t;
   }
@@ -556,7 +558,7 @@ void launch_layernorm_bwd(const void* dy, const void* x, const void* gamma, cons
 
 void launch_colsum_partial_reduce(const float* partial, int n_partial, int cols, void* out,
                                   int out_bf16, cudaStream_t stream) {
-  colsum_partial_reduce_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(partial, n_partial, cols, out,
+  colsum_partial_reduce_kernel<<<(cols + 31) / 32, 32 * kPrWarps, 0, stream>>>(partial, n_partial, cols, out,
                                                                     out_bf16, 0, nullptr);
 }
 
@@ -564,7 +566,7 @@ void launch_colsum_partial_reduce2(const float* partial, int n_partial, int cols
                                    void* out1, int out_bf16, cudaStream_t stream) {
   // partial = [2][n_partial][cols]; one launch reduces both halves
   dim3 grid((cols + 31) / 32, 2);
-  colsum_partial_reduce_kernel<<<grid, 256, 0, stream>>>(
+  colsum_partial_reduce_kernel<<<grid, 32 * kPrWarps, 0, stream>>>(
       partial, n_partial, cols, out0, out_bf16, static_cast<size_t>(n_partial) * cols, out1);
 }
 

@@ -214,6 +214,7 @@ __device__ __forceinline__ float sumsq_range(const void* x, size_t numel, size_t
   float acc = 0.f;
   const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   const size_t n4 = aligned ? numel / 4 : 0;
+#pragma unroll 4
   for (size_t i = tid; i < n4; i += stride) {
     float v[4];
     load4<kBf16>(x, i, v);
@@ -345,14 +346,14 @@ void launch_scale_(void* x, int dtype, size_t numel, float scale, const float* s
 void launch_sumsq_multi(const void* const* ptrs, const int64_t* numels, const int* dtypes,
                         int n_tensors, float* out, cudaStream_t stream) {
   if (n_tensors <= 0) return;
-  dim3 grid(32, n_tensors);
+  dim3 grid(148, n_tensors);         // one CTA column per SM: enough loads in flight for the big tensors
   sumsq_multi_kernel<<<grid, kThreads, 0, stream>>>(ptrs, numels, dtypes, out);
 }
 
 void launch_scale_multi(void* const* ptrs, const int64_t* numels, const int* dtypes, int n_tensors,
                         float scale, const float* scale_ptr, cudaStream_t stream) {
   if (n_tensors <= 0) return;
-  dim3 grid(32, n_tensors);
+  dim3 grid(148, n_tensors);
   scale_multi_kernel<<<grid, kThreads, 0, stream>>>(ptrs, numels, dtypes, scale, scale_ptr);
 }
 
