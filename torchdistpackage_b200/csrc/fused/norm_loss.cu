@@ -289,12 +289,21 @@ layernorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     const size_t base = static_cast<size_t>(row) * cols;
     const float mu = mean[row], rs = rstd[row];
     float xh[kVpl][8], dyv[kVpl][8];
+    uint4 xr[kVpl], dr[kVpl], rr[kVpl];
     float s1 = 0.f, s2 = 0.f;
+    // every load of the row is issued before the first use (the skip gradient included: loading
+    // it after the two reductions cost a third exposed memory round trip per row)
 #pragma unroll
     for (int i = 0; i < kVpl; ++i) {
       const int off = (lane + 32 * i) * 8;
-      unpack8(*reinterpret_cast<const uint4*>(x + base + off), xh[i]);
-      unpack8(*reinterpret_cast<const uint4*>(dy + base + off), dyv[i]);
+      xr[i] = *reinterpret_cast<const uint4*>(x + base + off);
+      dr[i] = *reinterpret_cast<const uint4*>(dy + base + off);
+      if (dresid) rr[i] = *reinterpret_cast<const uint4*>(dresid + base + off);
+    }
+#pragma unroll
+    for (int i = 0; i < kVpl; ++i) {
+      unpack8(xr[i], xh[i]);
+      unpack8(dr[i], dyv[i]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         xh[i][k] = (xh[i][k] - mu) * rs;
@@ -311,7 +320,7 @@ layernorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     for (int i = 0; i < kVpl; ++i) {
       const int off = (lane + 32 * i) * 8;
       float o[8], r[8];
-      if (dresid) unpack8(*reinterpret_cast<const uint4*>(dresid + base + off), r);
+      if (dresid) unpack8(rr[i], r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         o[k] = rs * (dyv[i][k] * g[i][k] - s1 - xh[i][k] * s2);

@@ -118,8 +118,10 @@ class GPT2(nn.Module):
 
     def embed(self, idx: torch.Tensor) -> torch.Tensor:
         T = idx.shape[1]
-        pos = torch.arange(T, device=idx.device)
-        return self.wte(idx) + self.wpe(pos)
+        # tied_embedding: the token-embedding gradient is scattered into the LM head's dense
+        # gradient (ops/fused.py); positions are a plain slice (its backward is a dense copy,
+        # not an index scatter)
+        return F_ops.tied_embedding(idx, self.wte.weight) + self.wpe.weight[:T]
 
     def head_loss(self, x: torch.Tensor, targets: Optional[torch.Tensor]):
         x = F_ops.layer_norm(x, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps)

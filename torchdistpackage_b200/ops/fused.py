@@ -176,6 +176,8 @@ class _LmHeadLossFn(torch.autograd.Function):
         d_w = L.gemm(logits, h2, trans_a=True)                          # [V, D]
         ctx.save_for_backward(d_h, d_w)
         ctx.h_shape = hidden.shape
+        import weakref
+        ctx.weight_ref = weakref.ref(weight)
         return loss_rows.sum() / float(num_valid)
 
     @staticmethod
@@ -185,7 +187,50 @@ class _LmHeadLossFn(torch.autograd.Function):
         s = dloss.reshape(1).float()
         C.scale_(d_h.view(-1), 1.0, s)
         C.scale_(d_w.view(-1), 1.0, s)
+        # tied embedding: the embedding backward (last op of backward) adds its rows straight into
+        # this dense gradient (`tied_embedding`) instead of building a second [vocab, d] tensor
+        w = ctx.weight_ref()
+        if w is not None:
+            w._tdp_pending_dw = d_w
         return d_h.view(ctx.h_shape), d_w, None, None, None
+
+
+class _TiedEmbeddingFn(torch.autograd.Function):
+    """Embedding lookup whose weight is tied to the LM head (GPT-2).  Backward scatters d(out)
+    rows into the LM head's dense weight gradient, which ``lm_head_loss`` left on the parameter:
+    one row-scatter kernel with bf16x2 atomics replaces autograd's zero-filled [vocab, d] tensor,
+    the sort-based embedding backward and the dense add of the two contributions."""
+
+    @staticmethod
+    def forward(ctx, idx, weight):
+        ctx.save_for_backward(idx)
+        import weakref
+        ctx.weight_ref = weakref.ref(weight)
+        ctx.wshape = weight.shape
+        return F.embedding(idx, weight)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        w = ctx.weight_ref()
+        pend = getattr(w, "_tdp_pending_dw", None) if w is not None else None
+        d2 = dout.reshape(-1, dout.shape[-1])
+        if pend is not None:
+            del w._tdp_pending_dw
+        C = native()
+        if pend is not None and C is not None and pend.is_cuda and pend.dtype == torch.bfloat16 \
+                and pend.shape == ctx.wshape and d2.dtype == torch.bfloat16 and pend.is_contiguous() \
+                and (pend.shape[1] * 2) % 16 == 0:
+            C.rows_scatter_add(pend, idx.reshape(-1).contiguous(), d2.contiguous())
+            return None, None            # already part of the LM head's gradient tensor
+        dw = torch.zeros(ctx.wshape, dtype=dout.dtype, device=dout.device)
+        dw.index_add_(0, idx.reshape(-1), d2)
+        return None, dw
+
+
+def tied_embedding(idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``F.embedding(idx, weight)`` for a weight that is also the LM head of ``lm_head_loss``."""
+    return _TiedEmbeddingFn.apply(idx, weight)
 
 
 def lm_head_loss(hidden: torch.Tensor, weight: torch.Tensor, target: torch.Tensor,
