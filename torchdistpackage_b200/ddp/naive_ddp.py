@@ -222,8 +222,10 @@ class _GradReducer:
                     if p.grad is not None:
                         view.copy_(p.grad)
                     p.grad = view
-                    if self.on_cuda and p.dim() == 2 and p.dtype == torch.bfloat16:
-                        # lets ops.linear.wgrad write the weight gradient straight into the bucket
+                    if self.on_cuda and p.dtype == torch.bfloat16 and p.numel() % 8 == 0 \
+                            and view.data_ptr() % 16 == 0:
+                        # lets ops.linear.wgrad / colsum_param / the LayerNorm backward write the
+                        # gradient straight into the bucket (weights, biases, LN parameters)
                         p._tdp_main_grad = view
                         p._tdp_grad_fresh = True
             self.buckets.append(bucket)

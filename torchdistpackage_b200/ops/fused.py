@@ -27,6 +27,26 @@ def _fused_ok(*ts) -> bool:
     return all(t is None or (t.is_cuda and t.dtype == torch.bfloat16) for t in ts)
 
 
+
+def _ln_param_grads(weight, bias_p, has_bias, cols, dev, wdtype):
+    """Output tensors for LayerNorm's dgamma / dbeta: the parameters' gradient-bucket views when a
+    reducer registered them and they are fresh (returns flags telling what autograd should get)."""
+    from .linear import direct_grad_buffer
+    gbuf, gfresh = direct_grad_buffer(weight) if weight is not None else (None, False)
+    bbuf, bfresh = direct_grad_buffer(bias_p) if (bias_p is not None and has_bias) else (None, False)
+    direct = gbuf is not None and gfresh and gbuf.dtype == wdtype and \
+        (not has_bias or (bbuf is not None and bfresh and bbuf.dtype == wdtype))
+    if direct:
+        dgamma = gbuf
+        dbeta = bbuf if has_bias else torch.empty(cols, dtype=wdtype, device=dev)
+        weight._tdp_grad_fresh = False
+        if has_bias:
+            bias_p._tdp_grad_fresh = False
+        return dgamma, dbeta, True
+    return (torch.empty(cols, dtype=wdtype, device=dev), torch.empty(cols, dtype=wdtype, device=dev),
+            False)
+
+
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps: float, residual):
@@ -41,6 +61,9 @@ class _LayerNormFn(torch.autograd.Function):
         native().layernorm_fwd(x2, r2, weight, bias, y, s, mean, rstd, float(eps))
         ctx.save_for_backward(s if residual is not None else x2, weight, mean, rstd)
         ctx.has_res, ctx.has_bias = residual is not None, bias is not None
+        import weakref
+        ctx.w_ref = weakref.ref(weight)
+        ctx.b_ref = weakref.ref(bias) if bias is not None else None
         ctx.shape = shape
         if residual is not None:
             return y.view(shape), s.view(shape)
@@ -53,10 +76,12 @@ class _LayerNormFn(torch.autograd.Function):
         dy2 = dy.reshape(rows, cols).contiguous()
         ds2 = ds.reshape(rows, cols).contiguous() if (ctx.has_res and ds is not None) else None
         dx = torch.empty_like(xin)
-        dgamma = torch.empty(cols, dtype=weight.dtype, device=xin.device)
-        dbeta = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        dgamma, dbeta, direct = _ln_param_grads(ctx.w_ref(), ctx.b_ref() if ctx.b_ref else None,
+                                                ctx.has_bias, cols, xin.device, weight.dtype)
         native().layernorm_bwd(dy2, xin, weight, mean, rstd, dx, ds2, dgamma, dbeta)
         dxv = dx.view(ctx.shape)
+        if direct:
+            return dxv, None, None, None, (dxv if ctx.has_res else None)
         return dxv, dgamma, (dbeta if ctx.has_bias else None), None, (dxv if ctx.has_res else None)
 
 
@@ -79,6 +104,9 @@ class _LayerNormForkFn(torch.autograd.Function):
         native().layernorm_fwd(x2, None, weight, bias, y, None, mean, rstd, float(eps))
         ctx.save_for_backward(x2, weight, mean, rstd)
         ctx.has_bias = bias is not None
+        import weakref
+        ctx.w_ref = weakref.ref(weight)
+        ctx.b_ref = weakref.ref(bias) if bias is not None else None
         ctx.shape = shape
         return y.view(shape), x.view(shape)
 
@@ -91,9 +119,11 @@ class _LayerNormForkFn(torch.autograd.Function):
         dy2 = dy.reshape(rows, cols).contiguous()
         ds2 = dskip.reshape(rows, cols).contiguous() if dskip is not None else None
         dx = torch.empty_like(xin)
-        dgamma = torch.empty(cols, dtype=weight.dtype, device=xin.device)
-        dbeta = torch.empty(cols, dtype=weight.dtype, device=xin.device)
+        dgamma, dbeta, direct = _ln_param_grads(ctx.w_ref(), ctx.b_ref() if ctx.b_ref else None,
+                                                ctx.has_bias, cols, xin.device, weight.dtype)
         native().layernorm_bwd(dy2, xin, weight, mean, rstd, dx, ds2, dgamma, dbeta)
+        if direct:
+            return dx.view(ctx.shape), None, None, None
         return dx.view(ctx.shape), dgamma, (dbeta if ctx.has_bias else None), None
 
 

@@ -15,6 +15,7 @@ of the fc2 dgrad GEMM (``ACT_DGELU``).  bf16 CUDA tensors take the native path; 
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -113,6 +114,31 @@ def colsum(x2d: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
     return out
 
 
+def direct_grad_buffer(p: torch.Tensor):
+    """``(bucket_view, overwrite)`` if parameter ``p``'s gradient can be written straight into the
+    gradient bucket a reducer registered on it (see :func:`wgrad`), else ``(None, False)``."""
+    buf = getattr(p, "_tdp_main_grad", None)
+    if buf is None or p.grad is None or p.grad.data_ptr() != buf.data_ptr() \
+            or getattr(p, "_tdp_no_fused_wgrad", False) or not _FUSED_WGRAD:
+        return None, False
+    return buf, bool(p._tdp_grad_fresh)
+
+
+def colsum_param(bias: torch.Tensor, x2d: torch.Tensor):
+    """Bias gradient ``x2d.sum(0)`` for parameter ``bias``: written straight into its gradient
+    bucket view when there is one (returns ``None`` to autograd: no temporary, no ``grad += db``
+    launch per bias -- 48 of those per GPT-2-small step), else returned as a tensor."""
+    buf, fresh = direct_grad_buffer(bias)
+    if buf is None or x2d.shape[1] % 8 != 0 or x2d.stride(1) != 1 or buf.dtype != torch.bfloat16:
+        return colsum(x2d, bias.dtype)
+    if fresh:
+        native(required=True).colsum(x2d, buf)
+        bias._tdp_grad_fresh = False
+    else:
+        buf.add_(colsum(x2d, buf.dtype))
+    return None
+
+
 def wgrad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
     """Weight gradient ``a^T @ b`` for parameter ``w``.
 
@@ -155,6 +181,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w, z)
         ctx.layout_nk, ctx.act = layout_nk, act
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.bias_ref = weakref.ref(bias) if bias is not None else None
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], N)
 
@@ -181,7 +208,8 @@ class _LinearFn(torch.autograd.Function):
             else:               # dW [K, N] = x^T @ dz
                 dw = wgrad(w, x2, dz)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dz)
+            b_ref = ctx.bias_ref() if ctx.bias_ref is not None else None
+            db = colsum_param(b_ref, dz) if b_ref is not None else colsum(dz)
         if ctx.has_res and ctx.needs_input_grad[5]:
             dres = dy
         return dx, dw, db, None, None, dres
@@ -218,6 +246,8 @@ class _MlpFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w1, w2, z, a)
         ctx.layout_nk, ctx.act = layout_nk, act
         ctx.flags = (b1 is not None, b2 is not None, residual is not None)
+        ctx.bias_refs = (weakref.ref(b1) if b1 is not None else None,
+                         weakref.ref(b2) if b2 is not None else None)
         ctx.x_shape = x.shape
         N = w2.shape[0] if layout_nk else w2.shape[1]
         return y.view(*x.shape[:-1], N)
@@ -231,10 +261,12 @@ class _MlpFn(torch.autograd.Function):
         # dz = (dy @ W2^T) * act'(z)   -- derivative applied in the epilogue
         dz = gemm(dy2, w2, trans_b=not nk, act=_DACT[ctx.act], aux_in=z)
         dw2 = wgrad(w2, dy2, a) if nk else wgrad(w2, a, dy2)
-        db2 = colsum(dy2) if has_b2 else None
+        rb1 = ctx.bias_refs[0]() if ctx.bias_refs[0] is not None else None
+        rb2 = ctx.bias_refs[1]() if ctx.bias_refs[1] is not None else None
+        db2 = (colsum_param(rb2, dy2) if rb2 is not None else colsum(dy2)) if has_b2 else None
         dx = gemm(dz, w1, trans_b=not nk).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
         dw1 = wgrad(w1, dz, x2) if nk else wgrad(w1, x2, dz)
-        db1 = colsum(dz) if has_b1 else None
+        db1 = (colsum_param(rb1, dz) if rb1 is not None else colsum(dz)) if has_b1 else None
         dres = dy if has_res else None
         return dx, dw1, db1, dw2, db2, None, None, dres
 
