@@ -68,6 +68,15 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
   }
   auto fn = get_encode_fn();
   if (!fn) return false;
+  // worker threads (autograd engine) may not have a current context yet: the driver entry point
+  // below needs one.  Bind it once per thread (cudaSetDevice is legal during stream capture).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    cudaSetDevice(dev0);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
