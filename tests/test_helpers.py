@@ -402,3 +402,43 @@ def test_grouped_mlp_coordinate_mapping(monkeypatch):
     assert torch.allclose(y, ref, atol=1e-10)
     for name, g_, w_ in zip(("dx", "dw1", "db1", "dw2", "db2"), got, want):
         assert torch.allclose(g_, w_, atol=1e-8), name
+
+
+def test_layer_norm_fork_and_tied_embedding_cpu_paths():
+    """CPU fallbacks of the two step-level fusions keep plain-autograd semantics: the skip alias of
+    layer_norm_fork carries gradient back to x, tied_embedding sums with the LM-head gradient."""
+    from torchdistpackage_b200.ops import fused as Fo
+    torch.manual_seed(0)
+    x = torch.randn(3, 5, 16, requires_grad=True)
+    w, b = torch.randn(16, requires_grad=True), torch.randn(16, requires_grad=True)
+    h, skip = Fo.layer_norm_fork(x, w, b)
+    (h.pow(2).sum() + (skip * 3).sum()).backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    (F.layer_norm(x2, (16,), w.detach(), b.detach()).pow(2).sum() + (x2 * 3).sum()).backward()
+    assert torch.allclose(x.grad, x2.grad, atol=1e-5)
+    # tied embedding: dense fallback (no pending LM-head gradient on the weight)
+    W = torch.randn(11, 4, requires_grad=True)
+    idx = torch.tensor([[1, 3, 3], [0, 10, 1]])
+    out = Fo.tied_embedding(idx, W)
+    (out * torch.arange(6.).view(2, 3, 1)).sum().backward()
+    W2 = W.detach().clone().requires_grad_(True)
+    (F.embedding(idx, W2) * torch.arange(6.).view(2, 3, 1)).sum().backward()
+    assert torch.allclose(W.grad, W2.grad)
+
+
+def test_multi_tensor_helpers_cpu_fallback():
+    from torchdistpackage_b200.ops.fused import multi_scale_, multi_sumsq
+    ts = [torch.randn(7), torch.randn(3, 5), torch.zeros(0)]
+    ref = sum(float(t.pow(2).sum()) for t in ts)
+    assert abs(float(multi_sumsq(ts)[0]) - ref) < 1e-4
+    before = [t.clone() for t in ts]
+    multi_scale_(ts, 0.5, torch.tensor([4.0]))
+    for t, b in zip(ts, before):
+        assert torch.allclose(t, b * 2.0)
+
+
+def test_node_group_rank_lists():
+    from torchdistpackage_b200.dist.node_group import inter_node_rank_lists, node_rank_lists
+    assert node_rank_lists(8, 8) is None and inter_node_rank_lists(8, 8) is None
+    assert node_rank_lists(16, 8) == [list(range(8)), list(range(8, 16))]
+    assert inter_node_rank_lists(16, 8) == [[i, i + 8] for i in range(8)]
