@@ -232,6 +232,10 @@ def grad_check_ours(step, batch, world, device):
     opt.set_lr(0.0)
     tokens, targets = batch[:, :-1], batch[:, 1:]
     fused = bool(getattr(opt, "fused_comm", False))
+    if os.environ.get("TDP_BENCH_GPU_LAG"):
+        # debugging aid: let the host run far ahead of the device (as it does on a loaded 8-GPU
+        # box), which exposes any missing device-side ordering between the streams
+        torch.cuda._sleep(int(float(os.environ["TDP_BENCH_GPU_LAG"]) * 1.9e9))
     if fused:
         # fused reduce-scatter -> AdamW -> all-gather kernels never materialise the averaged
         # gradient; the same kernels run once (eagerly) with their write-back flag on
@@ -252,13 +256,27 @@ def grad_check_ours(step, batch, world, device):
     finally:
         red._reduce_bucket = orig
     worst_max, worst_l2, sym = 0.0, 0.0, 0
+    detail = []
     for b, g in zip(red.buckets, got):
-        ref = b.payload().float().clone()
+        local = b.payload().float().clone()
+        ref = local.clone()
         dist.all_reduce(ref, group=b.group)
         ref /= world
-        worst_max = max(worst_max, float((g - ref).abs().max() / ref.abs().max().clamp_min(1e-20)))
-        worst_l2 = max(worst_l2, float((g - ref).norm() / ref.norm().clamp_min(1e-20)))
+        e_max = float((g - ref).abs().max() / ref.abs().max().clamp_min(1e-20))
+        e_l2 = float((g - ref).norm() / ref.norm().clamp_min(1e-20))
+        worst_max, worst_l2 = max(worst_max, e_max), max(worst_l2, e_l2)
         sym += int(b.symm is not None)
+        if os.environ.get("TDP_BENCH_GRAD_DETAIL"):
+            bad = (g - ref).abs() > 0.05 * ref.abs().max()
+            nb = int(bad.sum())
+            idx = bad.nonzero().flatten()
+            detail.append(dict(bucket=b.index, numel=int(g.numel()), names=b.names[:2], rel=e_max, l2=e_l2,
+                               n_bad=nb, first_bad=int(idx[0]) if nb else -1, last_bad=int(idx[-1]) if nb else -1,
+                               got_vs_local_l2=float((g - local).norm() / local.norm().clamp_min(1e-20)),
+                               got_norm=float(g.norm()), ref_norm=float(ref.norm()), local_norm=float(local.norm())))
+    if detail:
+        import torch.distributed as _d
+        print(f"[grad detail rank {_d.get_rank()}] " + json.dumps(detail), file=sys.stderr, flush=True)
     opt.set_lr(lr0)
     # replicas must hold bit-identical parameters after all those steps (the fused path
     # multicasts them; a lost store would show up here)
@@ -274,9 +292,11 @@ def grad_check_ours(step, batch, world, device):
             "grad_check_buckets": len(red.buckets), "grad_check_symmetric_buckets": sym,
             "grad_check_how": ("the step's own reduction kernels (direct wgrad -> NVLS reduce; fused "
                                "optimizer mode: run eagerly with the averaged gradient written "
-                               "back) vs local grads averaged by NCCL all_reduce, same batch, "
-                               "lr=0; max over buckets and ranks of max|diff|/max|ref| and of "
-                               "the L2 ratio")}
+                               "back) vs local grads of a second backward pass averaged by NCCL "
+                               "all_reduce, same batch, lr=0; max over buckets and ranks of "
+                               "max|diff|/max|ref| and of the L2 ratio (the two passes differ by "
+                               "their own atomics: bf16 row scatter of the tied embedding, fp32 "
+                               "column sums)")}
 
 
 def exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms_with_comm):
@@ -286,8 +306,13 @@ def exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms_with_comm):
     from torchdistpackage_b200.ops.graph import GraphedStep
     ctx = build_ours.ctx
     red = ctx["ddp"].reducer
+    opt = ctx["opt"]
     orig = red._reduce_bucket
     red._reduce_bucket = lambda bucket: setattr(bucket, "reduced", True)
+    # the replicas see un-averaged gradients in this run: freeze the weights (lr = 0 -- the
+    # optimizer kernels still run, with identical cost) so that they cannot drift apart
+    lr0 = float(opt.param_groups[0]["lr"])
+    opt.set_lr(0.0)
     try:
         b0 = dev_batches[0]
         if ctx["args"].no_graph:
@@ -308,6 +333,7 @@ def exposed_comm_ours(dev_batches, K, barrier, max_over_ranks, ms_with_comm):
         ms = max_over_ranks(s.elapsed_time(e)) / K
     finally:
         red._reduce_bucket = orig
+        opt.set_lr(lr0)
     del g
     return {"exposed_comm_ms": ms_with_comm - ms, "ms_per_step_without_collective": ms}
 

@@ -184,6 +184,9 @@ void launch_cast_copy(void* dst, int dst_dtype, const void* src, int src_dtype, 
 // dst[idx[r], :] += src[r, :] for bf16 rows of row_bytes (multiple of 16) bytes (fused/layout.cu)
 void launch_rows_scatter_add_bf16(const void* src, void* dst, const long* idx, int n_rows,
                                   int row_bytes, long dst_rows, cudaStream_t stream);
+void launch_rows_copy3(const void* const* src, void* const* dst, int n0, int n1, int n2,
+                       int row_bytes, long s0, long s1, long s2, long d0, long d1, long d2,
+                       cudaStream_t stream);
 void launch_rows_copy(const void* src, void* dst, int n0, int n1, int n2, int row_bytes, long s0,
                       long s1, long s2, long d0, long d1, long d2, cudaStream_t stream);
 

@@ -26,6 +26,29 @@ rows_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n0,
   }
 }
 
+// three sources with identical strides into three destination windows of one tensor (dq | dk | dv
+// -> packed dqkv): blockIdx.y selects the source, one launch instead of three
+struct Rows3 {
+  const uint4* src[3];
+  uint4* dst[3];
+};
+__global__ void __launch_bounds__(256)
+rows_copy3_kernel(Rows3 p, int n0, int n1, int n2, int vec_per_row, long s0, long s1, long s2,
+                  long d0, long d1, long d2) {
+  const uint4* __restrict__ src = p.src[blockIdx.y];
+  uint4* __restrict__ dst = p.dst[blockIdx.y];
+  const long total = static_cast<long>(n0) * n1 * n2 * vec_per_row;
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int v = static_cast<int>(i % vec_per_row);
+    long r = i / vec_per_row;
+    const int i2 = static_cast<int>(r % n2); r /= n2;
+    const int i1 = static_cast<int>(r % n1);
+    const int i0 = static_cast<int>(r / n1);
+    dst[i0 * d0 + i1 * d1 + i2 * d2 + v] = src[i0 * s0 + i1 * s1 + i2 * s2 + v];
+  }
+}
+
 // dst[idx[r], :] += src[r, :]  (bf16, rows of `vec_per_row` 16-byte vectors): the embedding
 // weight gradient scattered straight into an existing dense gradient -- no [vocab, d] zero-fill,
 // no sort, no second dense add.  One warp per token row, packed bf16x2 atomics (red.global).
@@ -59,6 +82,22 @@ void launch_rows_scatter_add_bf16(const void* src, void* dst, const long* idx, i
   rows_scatter_add_bf16_kernel<<<blocks, 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(src), reinterpret_cast<__nv_bfloat162*>(dst), idx, n_rows,
       row_bytes / 16, dst_rows);
+}
+
+void launch_rows_copy3(const void* const* src, void* const* dst, int n0, int n1, int n2,
+                       int row_bytes, long s0, long s1, long s2, long d0, long d1, long d2,
+                       cudaStream_t stream) {
+  const long total = static_cast<long>(n0) * n1 * n2 * (row_bytes / 16);
+  if (total <= 0) return;
+  long blocks = (total + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  Rows3 p;
+  for (int i = 0; i < 3; ++i) {
+    p.src[i] = reinterpret_cast<const uint4*>(src[i]);
+    p.dst[i] = reinterpret_cast<uint4*>(dst[i]);
+  }
+  rows_copy3_kernel<<<dim3(static_cast<int>(blocks), 3), 256, 0, stream>>>(
+      p, n0, n1, n2, row_bytes / 16, s0 / 16, s1 / 16, s2 / 16, d0 / 16, d1 / 16, d2 / 16);
 }
 
 void launch_rows_copy(const void* src, void* dst, int n0, int n1, int n2, int row_bytes,

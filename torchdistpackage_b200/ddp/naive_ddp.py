@@ -61,6 +61,9 @@ class GradBucket:
         # set by BucketAdamW(fused_comm=True): replaces the all-reduce of this bucket with the
         # fused reduce-scatter -> AdamW -> all-gather kernel
         self.fused_step = None
+        # streams on which directly written gradients of this bucket were produced (ops.linear
+        # note_grad_stream): the reduction is ordered behind each of them
+        self.producer_streams = set()
 
     # ---- layout
     def elem_align(self) -> int:
@@ -247,13 +250,17 @@ class _GradReducer:
             h.remove()
         self._hooks = []
         for p in self.params.values():
-            for attr in ("_tdp_main_grad", "_tdp_grad_fresh", "_tdp_reducer"):
+            for attr in ("_tdp_main_grad", "_tdp_grad_fresh", "_tdp_reducer", "_tdp_grad_stream"):
                 if hasattr(p, attr):
                     delattr(p, attr)
 
     def _on_grad_ready(self, name: str, p: torch.Tensor) -> None:
         bucket = self.param_bucket[name]
         self._finalized = False
+        gs = getattr(p, "_tdp_grad_stream", None)
+        if gs is not None:
+            bucket.producer_streams.add(gs)
+            p._tdp_grad_stream = None
         if self.as_view:
             view = bucket.views[name]
             if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
@@ -302,6 +309,10 @@ class _GradReducer:
         if self.on_cuda:
             cur = torch.cuda.current_stream(self.device)
             self.comm_stream.wait_stream(cur)       # device-side dependency only
+            for ps in bucket.producer_streams:      # gradients written outside autograd's view
+                if ps != cur:
+                    self.comm_stream.wait_stream(ps)
+            bucket.producer_streams.clear()
             self._comm_used = True
             with torch.cuda.stream(self.comm_stream):
                 self._pack(bucket)

@@ -57,10 +57,12 @@ class _PackedAttnFn(torch.autograd.Function):
             C.permute_rows_copy(do, dview)
         dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
         dqkv = torch.empty(B, T, 3, H, dh, dtype=dout.dtype, device=dout.device)
-        for i, g in enumerate((dq, dk, dv)):
-            if g.stride(3) != 1:
-                g = g.contiguous()
-            C.permute_rows_copy(dqkv[:, :, i].transpose(1, 2), g)
+        gs = [g if g.stride(3) == 1 else g.contiguous() for g in (dq, dk, dv)]
+        dsts = [dqkv[:, :, i].transpose(1, 2) for i in range(3)]
+        # one launch packs all three (falls back to one launch each if their strides differ)
+        if not (hasattr(C, "permute_rows_copy3") and C.permute_rows_copy3(dsts, gs)):
+            for d, g in zip(dsts, gs):
+                C.permute_rows_copy(d, g)
         return dqkv.view(B, T, 3 * H * dh), None, None, None
 
 

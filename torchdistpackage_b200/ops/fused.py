@@ -37,11 +37,14 @@ def _ln_param_grads(weight, bias_p, has_bias, cols, dev, wdtype):
     direct = gbuf is not None and gfresh and gbuf.dtype == wdtype and \
         (not has_bias or (bbuf is not None and bfresh and bbuf.dtype == wdtype))
     if direct:
+        from .linear import note_grad_stream
         dgamma = gbuf
         dbeta = bbuf if has_bias else torch.empty(cols, dtype=wdtype, device=dev)
         weight._tdp_grad_fresh = False
+        note_grad_stream(weight)
         if has_bias:
             bias_p._tdp_grad_fresh = False
+            note_grad_stream(bias_p)
         return dgamma, dbeta, True
     return (torch.empty(cols, dtype=wdtype, device=dev), torch.empty(cols, dtype=wdtype, device=dev),
             False)

@@ -114,6 +114,19 @@ def colsum(x2d: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
     return out
 
 
+def note_grad_stream(p: torch.Tensor) -> None:
+    """Remember the stream on which ``p``'s gradient was just written into its bucket view.
+
+    A parameter whose backward returns ``None`` (direct route) gives autograd nothing to
+    synchronise: its post-accumulate hook runs with whatever stream the parameter's AccumulateGrad
+    node is bound to -- the stream that was current when the node was created (e.g. a CUDA-graph
+    warm-up side stream), not necessarily the stream the producing kernel was enqueued on.  The
+    reducer therefore orders its comm stream behind this stream explicitly (found with a device-lag
+    experiment: without it the bucket kernel could run before the weight-gradient GEMMs)."""
+    if p.is_cuda:
+        p._tdp_grad_stream = torch.cuda.current_stream(p.device)
+
+
 def direct_grad_buffer(p: torch.Tensor):
     """``(bucket_view, overwrite)`` if parameter ``p``'s gradient can be written straight into the
     gradient bucket a reducer registered on it (see :func:`wgrad`), else ``(None, False)``."""
@@ -136,6 +149,7 @@ def colsum_param(bias: torch.Tensor, x2d: torch.Tensor):
         bias._tdp_grad_fresh = False
     else:
         buf.add_(colsum(x2d, buf.dtype))
+    note_grad_stream(bias)
     return None
 
 
@@ -158,6 +172,7 @@ def wgrad(w: torch.Tensor, a: torch.Tensor, b: torch.Tensor):
         w._tdp_grad_fresh = False
     else:
         gemm(a, b, trans_a=True, out=buf, accumulate=True)
+    note_grad_stream(w)
     return None
 
 
