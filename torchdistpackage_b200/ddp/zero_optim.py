@@ -60,6 +60,7 @@ class _ZBucket:
         self.start = start
         self.numel = numel
         self.slice = numel // world
+        self.master_off = 0          # offset of this bucket's slice inside the group's master shard
         self.params: List[torch.nn.Parameter] = []
         self.ready = 0
         self.reduced = False
@@ -211,6 +212,10 @@ class Bf16ZeroOptimizer:
                 self.buckets.append(_ZBucket(len(self.buckets), gi, start, bs, self.world))
                 start += bs
             group_buckets = self.buckets[first_bucket:]
+            o = 0
+            for b in group_buckets:
+                b.master_off = o
+                o += b.slice
 
             # re-home parameters and gradients into the flat buffers
             with torch.no_grad():
@@ -289,14 +294,7 @@ class Bf16ZeroOptimizer:
         return flat[lo:lo + b.slice]
 
     def _master_slice(self, b: _ZBucket, t: torch.Tensor) -> torch.Tensor:
-        o = 0
-        for bb in self.buckets:
-            if bb.group_idx != b.group_idx:
-                continue
-            if bb is b:
-                return t[o:o + b.slice]
-            o += bb.slice
-        raise RuntimeError("bucket not found")
+        return t[b.master_off:b.master_off + b.slice]
 
     def _reduce_bucket(self, b: _ZBucket) -> None:
         """Reduce-scatter bucket ``b``: averaged slice -> master grad (fp32)."""
