@@ -78,154 +78,365 @@ def wait(pred):
 
 
 # ------------------------------------------------------------------------------------------------
-# forward: mirrors attn_fwd_sm100.cu
+# forward: mirrors attn_fwd_sm100.cu (persistent CTA walking several work items; double-buffered
+# Q; K / V rings that run across items; S released to the tensor core as soon as it is in
+# registers; the MMA thread serves the two groups' events in arrival order with non-blocking tests)
 # ------------------------------------------------------------------------------------------------
-def forward_roles(n_kv, stages=3):
-    n_max = max(n_kv)
+class Machine:
+    """Barriers, buffers and the in-order tensor-core completion queue shared by the roles."""
+
+    def __init__(self):
+        self.pending = []
+        self.mma_done = False
+
+    def commit(self, bars, releases=()):
+        # tcgen05.commit: arrives once every MMA issued so far has completed; MMAs complete lazily
+        # (in issue order) to expose missing waits
+        self.pending.append((list(bars), list(releases)))
+
+    def engine(self):
+        while True:
+            if self.pending:
+                bars, rel = self.pending.pop(0)
+                for r in rel:
+                    r.end_read()
+                for b in bars:
+                    b.arrive()
+                yield True
+            else:
+                yield False
+                if self.mma_done and not self.pending:
+                    return
+
+
+def forward_roles(items, stages=3, rescale_prob=0.3, seed=0):
+    """items: list of (n_kv0, n_kv1) per work item of this CTA."""
+    rng = random.Random(1000 + seed)
+    M = Machine()
+    q_full, q_empty = [MBar(1), MBar(1)], [MBar(1), MBar(1)]
     k_full = [MBar(1) for _ in range(stages)]
     k_empty = [MBar(1) for _ in range(stages)]
     v_full = [MBar(1) for _ in range(stages)]
     v_empty = [MBar(1) for _ in range(stages)]
-    s_full = [MBar(1), MBar(1)]
-    p_ready = [MBar(4), MBar(4)]
-    o_full = [MBar(1), MBar(1)]
+    s_full, s_free = [MBar(1), MBar(1)], [MBar(4), MBar(4)]
+    p_ready, o_full = [MBar(4), MBar(4)], [MBar(1), MBar(1)]
+    Q = [Resource("Q buf0"), Resource("Q buf1")]
     K = [Resource(f"K{s}") for s in range(stages)]
     V = [Resource(f"V{s}") for s in range(stages)]
-    S = [Resource("S0"), Resource("S1")]
-    P = [Resource("P0"), Resource("P1")]
-    O = [Resource("O0'"), Resource("O1'")]
-    pending = []        # (bars to arrive, resources to release) of MMAs not yet "completed"
-
-    def commit(bars, releases=()):
-        # tcgen05.commit: arrives once every MMA issued so far has completed; the model completes
-        # MMAs lazily (in issue order) to expose missing waits
-        pending.append((list(bars), list(releases)))
-
-    def mma_engine():
-        while True:
-            if pending:
-                bars, rel = pending.pop(0)
-                for r in rel:
-                    r.end_read()
-                for b in bars:
-                    b.arrive()
-                yield True
-            else:
-                yield False
-                if done["mma"] and not pending:
-                    return
-
-    done = {"mma": False}
+    S = [Resource("S0 (TMEM)"), Resource("S1 (TMEM)")]
+    P = [Resource("P0 (smem)"), Resource("P1 (smem)")]
+    O = [Resource("O0 (TMEM)"), Resource("O1 (TMEM)")]
 
     def producer():
-        for j in range(n_max):
-            st, ph = j % stages, (j // stages) & 1
-            yield from wait(lambda: k_empty[st].passed_fresh(ph ^ 1))
-            K[st].write(j)
-            k_full[st].arrive()
-            yield from wait(lambda: v_empty[st].passed_fresh(ph ^ 1))
-            V[st].write(j)
-            v_full[st].arrive()
-            yield True
-
-    def issue_s(w, j):
-        st = j % stages
-        K[st].begin_read(j)
-        S[w].write(j)
-        commit([s_full[w]], [K[st]])
+        g = 0
+        for r, n_kv in enumerate(items):
+            qb = r & 1
+            if r >= 2:
+                yield from wait(lambda: q_empty[qb].passed(((r >> 1) - 1) & 1))
+            Q[qb].write(r)
+            q_full[qb].arrive()
+            for _ in range(max(n_kv)):
+                st, ph = g % stages, (g // stages) & 1
+                yield from wait(lambda: k_empty[st].passed_fresh(ph ^ 1))
+                K[st].write(g)
+                k_full[st].arrive()
+                yield from wait(lambda: v_empty[st].passed_fresh(ph ^ 1))
+                V[st].write(g)
+                v_full[st].arrive()
+                g += 1
+                yield True
 
     def mma():
-        if n_max > 0:
-            yield from wait(lambda: k_full[0].passed(0))
-            for w in range(2):
+        g = 0
+        a_cnt, b_cnt = [0, 0], [0, 0]
+        for r, n_kv in enumerate(items):
+            n_max, qb = max(n_kv), r & 1
+            a_loc, b_loc, s_iss = [0, 0], [0, 0], [0, 0]
+            rel = {"rk": 0, "rv": 0, "q": False}
+
+            def issue_s(w, j):
+                st = (g + j) % stages
+                K[st].begin_read(g + j)
+                Q[qb].begin_read(r)
+                S[w].write((r, j))               # asserts that nobody still reads S_w
+                M.commit([s_full[w]], [K[st], Q[qb]])
+                s_iss[w] = j + 1
+
+            def release():
+                while rel["rk"] < n_max and all(s_iss[w] > rel["rk"] or rel["rk"] >= n_kv[w] for w in (0, 1)):
+                    M.commit([k_empty[(g + rel["rk"]) % stages]])
+                    rel["rk"] += 1
+                while rel["rv"] < n_max and all(b_loc[w] > rel["rv"] or rel["rv"] >= n_kv[w] for w in (0, 1)):
+                    M.commit([v_empty[(g + rel["rv"]) % stages]])
+                    rel["rv"] += 1
+                if not rel["q"] and all(s_iss[w] >= n_kv[w] for w in (0, 1)):
+                    M.commit([q_empty[qb]])
+                    rel["q"] = True
+
+            yield from wait(lambda: q_full[qb].passed((r >> 1) & 1))
+            yield from wait(lambda: k_full[g % stages].passed((g // stages) & 1))
+            for w in (0, 1):
                 if n_kv[w] > 0:
                     issue_s(w, 0)
-            commit([k_empty[0]])
-        for j in range(n_max):
-            st, st1 = j % stages, (j + 1) % stages
-            ph, ph1 = (j // stages) & 1, ((j + 1) // stages) & 1
-            yield from wait(lambda: v_full[st].passed(ph))
-            if j + 1 < n_max:
-                yield from wait(lambda: k_full[st1].passed(ph1))
-            for w in range(2):
-                if j >= n_kv[w]:
-                    continue
-                yield from wait(lambda: p_ready[w].passed(j & 1))
-                P[w].begin_read(j)
-                V[st].begin_read(j)
-                O[w].write(j)
-                commit([o_full[w]], [P[w], V[st]])
-                if j + 1 < n_kv[w]:
-                    issue_s(w, j + 1)
-            commit([v_empty[st]])
-            if j + 1 < n_max:
-                commit([k_empty[st1]])
-            yield True
-        done["mma"] = True
+            release()
+            while any(a_loc[w] < n_kv[w] or b_loc[w] < n_kv[w] for w in (0, 1)):
+                progressed = False
+                for w in (0, 1):
+                    if a_loc[w] < n_kv[w] and s_free[w].passed(a_cnt[w] & 1):
+                        j = a_loc[w]
+                        gj = g + j + 1
+                        if j + 1 >= n_kv[w]:
+                            a_cnt[w] += 1; a_loc[w] += 1; progressed = True
+                        elif k_full[gj % stages].passed((gj // stages) & 1):
+                            a_cnt[w] += 1; a_loc[w] += 1; progressed = True
+                            issue_s(w, j + 1)
+                            release()
+                    if b_loc[w] < n_kv[w] and p_ready[w].passed(b_cnt[w] & 1):
+                        j = b_loc[w]
+                        gj = g + j
+                        if v_full[gj % stages].passed((gj // stages) & 1):
+                            b_cnt[w] += 1; progressed = True
+                            P[w].begin_read((r, j))
+                            V[gj % stages].begin_read(gj)
+                            O[w].write((r, j))       # asserts that nobody still reads O_w
+                            M.commit([o_full[w]], [P[w], V[gj % stages]])
+                            b_loc[w] = j + 1
+                            release()
+                yield progressed
+            g += n_max
+        M.mma_done = True
 
     def softmax(w):
-        for j in range(n_kv[w]):
-            yield from wait(lambda: s_full[w].passed(j & 1))
-            S[w].begin_read(j)
-            yield True                                   # pass A
-            if j > 0:
-                yield from wait(lambda: o_full[w].passed((j - 1) & 1))
-                O[w].begin_read(j - 1)
+        cnt_s = cnt_o = 0
+        store_pending = False
+        for r, n_kv in enumerate(items):
+            n_mine = n_kv[w]
+            for j in range(n_mine):
+                yield from wait(lambda: s_full[w].passed(cnt_s & 1))
+                cnt_s += 1
+                S[w].begin_read((r, j))
+                yield True                               # tcgen05.ld of the whole row
+                S[w].end_read()
+                for _ in range(4):
+                    s_free[w].arrive()                   # S_w lives in registers now
+                pv_done = j == 0
+                if j > 0 and rng.random() < rescale_prob:   # rare path: rescale O in TMEM
+                    yield from wait(lambda: o_full[w].passed(cnt_o & 1))
+                    cnt_o += 1
+                    pv_done = True
+                    O[w].begin_read((r, j - 1))
+                    yield True
+                    O[w].end_read()
+                yield True                               # exponentials
+                if not pv_done:
+                    yield from wait(lambda: o_full[w].passed(cnt_o & 1))
+                    cnt_o += 1
+                if store_pending:                        # output tile of the previous item left
+                    P[w].end_read()
+                    store_pending = False
+                P[w].write((r, j))                       # asserts that P.V(j-1) finished reading
+                for _ in range(4):
+                    p_ready[w].arrive()
+                yield True
+            if n_mine > 0:
+                yield from wait(lambda: o_full[w].passed(cnt_o & 1))
+                cnt_o += 1
+                O[w].begin_read((r, n_mine - 1))
+                yield True
                 O[w].end_read()
-            yield True                                   # pass B
-            P[w].write(j)
-            S[w].end_read()
-            for _ in range(4):
-                p_ready[w].arrive()
-            yield True
-        if n_kv[w] > 0:
-            yield from wait(lambda: o_full[w].passed((n_kv[w] - 1) & 1))
-            O[w].begin_read(n_kv[w] - 1)
-            O[w].end_read()
-            P[w].write(-2)                               # staging for the output tile
+                P[w].write(("out", r))                   # staging for the output tile
+                P[w].begin_read(("out", r))              # ... which the TMA store now reads
+                store_pending = True
+        if store_pending:
+            P[w].end_read()
 
-    return [producer(), mma(), mma_engine(), softmax(0), softmax(1)]
+    return [producer(), mma(), M.engine(), softmax(0), softmax(1)]
 
 
-@pytest.mark.parametrize("n_kv", [(1, 0), (1, 2), (2, 3), (4, 5), (8, 8), (3, 3), (7, 8)])
-def test_forward_protocol(n_kv):
+@pytest.mark.parametrize("items", [
+    [(1, 0)], [(1, 2)], [(2, 3), (1, 2)], [(4, 5), (3, 4), (1, 2)], [(8, 8), (8, 8)],
+    [(7, 8), (5, 6), (3, 4), (1, 2), (1, 2)], [(3, 3), (1, 0), (2, 2)], [(1, 2)] * 6])
+def test_forward_protocol(items):
     for seed in range(40):
-        run(forward_roles(list(n_kv)), seed)
+        run(forward_roles(list(items), seed=seed), seed)
+
+
+def test_forward_protocol_detects_a_missing_wait():
+    """The model must be able to fail: drop the wait for P.V(j-1) before overwriting the P tile."""
+    import types
+    src = forward_roles.__code__
+    bad = forward_roles.__globals__.copy()
+    import inspect
+    text = inspect.getsource(forward_roles).replace(
+        "                if not pv_done:\n"
+        "                    yield from wait(lambda: o_full[w].passed(cnt_o & 1))\n"
+        "                    cnt_o += 1\n", "                cnt_o += 0 if pv_done else 1\n")
+    assert text != inspect.getsource(forward_roles)
+    exec(text.replace("def forward_roles", "def broken_roles"), bad)
+    with pytest.raises(AssertionError):
+        for seed in range(60):
+            run(bad["broken_roles"]([(6, 6), (6, 6)], seed=seed), seed)
 
 
 # ------------------------------------------------------------------------------------------------
-# backward: mirrors attn_bwd_sm100.cu
+# backward dQ: mirrors attn_bwd_dq_sm100.cu (same machinery; S' / dP' pairs, dQ accumulated in TMEM,
+# the dS tile doubles as the landing zone of O and as the staging tile of the dQ store)
+# ------------------------------------------------------------------------------------------------
+def dq_roles(items, stages=4, seed=0):
+    M = Machine()
+    q_full, q_empty = MBar(1), MBar(1)
+    k_full = [MBar(1) for _ in range(stages)]
+    k_empty = [MBar(1) for _ in range(stages)]
+    v_full = [MBar(1) for _ in range(stages)]
+    v_empty = [MBar(1) for _ in range(stages)]
+    s_full, s_free = [MBar(1), MBar(1)], [MBar(4), MBar(4)]
+    p_ready, dq_full, stage_free = [MBar(4), MBar(4)], [MBar(1), MBar(1)], [MBar(1), MBar(1)]
+    QDO = Resource("Q, dO tiles")
+    K = [Resource(f"K'{s}") for s in range(stages)]
+    V = [Resource(f"V'{s}") for s in range(stages)]
+    SDP = [Resource("S'0, dP'0 (TMEM)"), Resource("S'1, dP'1 (TMEM)")]
+    DS = [Resource("dS0 / O0 / dQ0 staging"), Resource("dS1 / O1 / dQ1 staging")]
+
+    def producer():
+        g = 0
+        n_store = [0, 0]
+        for r, n_sub in enumerate(items):
+            if r > 0:
+                yield from wait(lambda: q_empty.passed((r - 1) & 1))
+            n_q = 2 if n_sub[1] > 0 else 1
+            for w in range(n_q):
+                if n_store[w] > 0:
+                    yield from wait(lambda: stage_free[w].passed((n_store[w] - 1) & 1))
+            QDO.write(r)
+            for w in range(n_q):
+                DS[w].write(("O", r))                     # O_w lands in the dS tile
+                n_store[w] += 1
+            q_full.arrive()
+            for _ in range(max(n_sub)):
+                st, ph = g % stages, (g // stages) & 1
+                yield from wait(lambda: k_empty[st].passed_fresh(ph ^ 1))
+                K[st].write(g); k_full[st].arrive()
+                yield from wait(lambda: v_empty[st].passed_fresh(ph ^ 1))
+                V[st].write(g); v_full[st].arrive()
+                g += 1
+                yield True
+
+    def mma():
+        g = 0
+        a_cnt, b_cnt = [0, 0], [0, 0]
+        for r, n_sub in enumerate(items):
+            n_max = max(n_sub)
+            a_loc, b_loc, s_iss = [0, 0], [0, 0], [0, 0]
+            rel = {"rk": 0, "rv": 0, "q": False}
+
+            def issue_sdp(w, j):
+                st = (g + j) % stages
+                K[st].begin_read(g + j); V[st].begin_read(g + j); QDO.begin_read(r)
+                SDP[w].write((r, j))
+                M.commit([s_full[w]], [K[st], V[st], QDO])
+                s_iss[w] = j + 1
+
+            def release():
+                while rel["rk"] < n_max and all(b_loc[w] > rel["rk"] or rel["rk"] >= n_sub[w] for w in (0, 1)):
+                    M.commit([k_empty[(g + rel["rk"]) % stages]]); rel["rk"] += 1
+                while rel["rv"] < n_max and all(s_iss[w] > rel["rv"] or rel["rv"] >= n_sub[w] for w in (0, 1)):
+                    M.commit([v_empty[(g + rel["rv"]) % stages]]); rel["rv"] += 1
+                if not rel["q"] and all(s_iss[w] >= n_sub[w] for w in (0, 1)):
+                    M.commit([q_empty]); rel["q"] = True
+
+            yield from wait(lambda: q_full.passed(r & 1))
+            yield from wait(lambda: k_full[g % stages].passed((g // stages) & 1))
+            yield from wait(lambda: v_full[g % stages].passed((g // stages) & 1))
+            for w in (0, 1):
+                if n_sub[w] > 0:
+                    issue_sdp(w, 0)
+            release()
+            while any(a_loc[w] < n_sub[w] or b_loc[w] < n_sub[w] for w in (0, 1)):
+                progressed = False
+                for w in (0, 1):
+                    if a_loc[w] < n_sub[w] and s_free[w].passed(a_cnt[w] & 1):
+                        j, gj = a_loc[w], g + a_loc[w] + 1
+                        if j + 1 >= n_sub[w]:
+                            a_cnt[w] += 1; a_loc[w] += 1; progressed = True
+                        elif k_full[gj % stages].passed((gj // stages) & 1) \
+                                and v_full[gj % stages].passed((gj // stages) & 1):
+                            a_cnt[w] += 1; a_loc[w] += 1; progressed = True
+                            issue_sdp(w, j + 1)
+                            release()
+                    if b_loc[w] < n_sub[w] and p_ready[w].passed(b_cnt[w] & 1):
+                        b_cnt[w] += 1; progressed = True
+                        j = b_loc[w]
+                        st = (g + j) % stages
+                        assert K[st].version == g + j, "K'(j) was released before dQ(j) read it"
+                        DS[w].begin_read((r, j)); K[st].begin_read(g + j)
+                        M.commit([dq_full[w]], [DS[w], K[st]])
+                        b_loc[w] = j + 1
+                        release()
+                yield progressed
+            g += n_max
+        M.mma_done = True
+
+    def softmax(w):
+        cnt_s = cnt_dq = 0
+        for r, n_sub in enumerate(items):
+            n_mine = n_sub[w]
+            if n_mine == 0:
+                continue
+            yield from wait(lambda: q_full.passed(r & 1))
+            DS[w].begin_read(("O", r)); QDO.begin_read(r)  # delta = rowsum(dO . O) from smem
+            yield True
+            DS[w].end_read(); QDO.end_read()
+            for j in range(n_mine):
+                yield from wait(lambda: s_full[w].passed(cnt_s & 1))
+                cnt_s += 1
+                SDP[w].begin_read((r, j))
+                yield True
+                SDP[w].end_read()
+                for _ in range(4):
+                    s_free[w].arrive()
+                yield True
+                if j > 0:
+                    yield from wait(lambda: dq_full[w].passed(cnt_dq & 1))
+                    cnt_dq += 1
+                DS[w].write((r, j))                      # asserts that dQ(j-1) finished reading dS
+                for _ in range(4):
+                    p_ready[w].arrive()
+                yield True
+            yield from wait(lambda: dq_full[w].passed(cnt_dq & 1))
+            cnt_dq += 1
+            DS[w].write(("dQ", r))                       # staging of the output tile
+            DS[w].begin_read(("dQ", r))                  # TMA store
+            yield True
+            DS[w].end_read()                             # cp.async.bulk.wait_group.read
+            stage_free[w].arrive()
+
+    return [producer(), mma(), M.engine(), softmax(0), softmax(1)]
+
+
+@pytest.mark.parametrize("items", [
+    [(2, 0)], [(2, 4)], [(4, 6), (2, 4)], [(16, 16), (16, 16)], [(14, 16), (10, 12), (6, 8), (2, 4)],
+    [(2, 4)] * 5])
+def test_backward_dq_protocol(items):
+    for seed in range(40):
+        run(dq_roles(list(items), seed=seed), seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# backward dK / dV: mirrors attn_bwd_sm100.cu (one CTA per key tile; S / dP handed back to the
+# tensor core as soon as both softmax groups hold them in registers; P / dS double buffered)
 # ------------------------------------------------------------------------------------------------
 def backward_roles(n_iter, q_stages=2):
+    M = Machine()
     q_full = [MBar(1) for _ in range(q_stages)]
     q_empty = [MBar(1) for _ in range(q_stages)]
-    s_full = MBar(1)
-    p_ready = [MBar(4), MBar(4)]
+    s_full, sdp_free = MBar(1), MBar(8)
+    p_ready = [MBar(8), MBar(8)]
     pds_free = [MBar(1), MBar(1)]
-    dq_full, dq_free, dkv_full = MBar(1), MBar(4), MBar(1)
+    dkv_full = MBar(1)
     Q = [Resource(f"Q/dO{s}") for s in range(q_stages)]
-    SDP = Resource("S,dP")
-    PDS = [Resource("P,dS[0]"), Resource("P,dS[1]")]
-    DQ = Resource("dQ tile")
-    pending = []
-    done = {"mma": False}
-
-    def commit(bars, releases=()):
-        pending.append((list(bars), list(releases)))
-
-    def mma_engine():
-        while True:
-            if pending:
-                bars, rel = pending.pop(0)
-                for r in rel:
-                    r.end_read()
-                for b in bars:
-                    b.arrive()
-                yield True
-            else:
-                yield False
-                if done["mma"] and not pending:
-                    return
+    SDP = Resource("S,dP (TMEM)")
+    # each softmax group owns one key half of the P / dS buffers
+    PDS = [[Resource(f"P,dS[{u}] half {h}") for h in range(2)] for u in range(2)]
 
     def producer():
         for it in range(n_iter):
@@ -240,55 +451,47 @@ def backward_roles(n_iter, q_stages=2):
             yield from wait(lambda: q_full[0].passed(0))
             Q[0].begin_read(0)
             SDP.write(0)
-            commit([s_full], [Q[0]])
+            M.commit([s_full], [Q[0]])
         for it in range(n_iter):
             s, u = it % q_stages, it & 1
-            yield from wait(lambda: p_ready[u].passed((it >> 1) & 1))
+            yield from wait(lambda: sdp_free.passed(it & 1))      # S_i / dP_i are in registers
             if it + 1 < n_iter:
                 s1 = (it + 1) % q_stages
                 yield from wait(lambda: q_full[s1].passed(((it + 1) // q_stages) & 1))
                 Q[s1].begin_read(it + 1)
-                SDP.write(it + 1)
-                commit([s_full], [Q[s1]])
-            if it > 0:
-                yield from wait(lambda: dq_free.passed((it - 1) & 1))
-            PDS[u].begin_read(it)
+                SDP.write(it + 1)                                 # asserts nobody still reads S / dP
+                M.commit([s_full], [Q[s1]])
+            yield from wait(lambda: p_ready[u].passed((it >> 1) & 1))
+            for h in range(2):
+                PDS[u][h].begin_read(it)
             Q[s].begin_read(it)
-            DQ.write(it)
-            bars = [dq_full, pds_free[u], q_empty[s]] + ([dkv_full] if it == n_iter - 1 else [])
-            commit(bars, [PDS[u], Q[s]])
+            bars = [pds_free[u], q_empty[s]] + ([dkv_full] if it == n_iter - 1 else [])
+            M.commit(bars, [PDS[u][0], PDS[u][1], Q[s]])
             yield True
-        done["mma"] = True
+        M.mma_done = True
 
-    def softmax():
+    def softmax(wg):
         for it in range(n_iter):
             u = it & 1
-            if it >= 2:
-                yield from wait(lambda: pds_free[u].passed(((it - 2) >> 1) & 1))
             yield from wait(lambda: s_full.passed(it & 1))
             SDP.begin_read(it)
-            yield True
-            PDS[u].write(it)
+            yield True                                            # tcgen05.ld of my column half
             SDP.end_read()
+            for _ in range(4):
+                sdp_free.arrive()
+            yield True                                            # exponentials, dS
+            if it >= 2:
+                yield from wait(lambda: pds_free[u].passed(((it - 2) >> 1) & 1))
+            PDS[u][wg].write(it)                                  # asserts dV / dK(it-2) finished
             for _ in range(4):
                 p_ready[u].arrive()
             yield True
         if n_iter > 0:
             yield from wait(lambda: dkv_full.passed(0))
-            for s in range(q_stages):
-                Q[s].write(-2)                           # staging for dK / dV
-
-    def drain():
-        for it in range(n_iter):
-            yield from wait(lambda: dq_full.passed(it & 1))
-            DQ.begin_read(it)
-            yield True
-            DQ.end_read()
-            for _ in range(4):
-                dq_free.arrive()
+            Q[0].write(-2 - wg) if wg == 0 else None              # staging for dV (group 0) ...
             yield True
 
-    return [producer(), mma(), mma_engine(), softmax(), drain()]
+    return [producer(), mma(), M.engine(), softmax(0), softmax(1)]
 
 
 @pytest.mark.parametrize("n_iter", [1, 2, 3, 4, 5, 8])
