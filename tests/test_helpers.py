@@ -228,6 +228,14 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
     monkeypatch.setattr(L, "colsum", lambda x, out_dtype=torch.bfloat16: x.float().sum(0).to(out_dtype))
     monkeypatch.setattr(L, "_FUSED_WGRAD", True)
 
+    class FakeNative:                               # colsum_param's direct write (bias gradients)
+        @staticmethod
+        def colsum(x, out):
+            out.copy_(x.float().sum(0).to(out.dtype))
+    monkeypatch.setattr(L, "native", lambda required=False: FakeNative)
+    # on CUDA the helpers remember the stream the gradient was written on; emulate that
+    monkeypatch.setattr(L, "note_grad_stream", lambda p: setattr(p, "_tdp_grad_stream", "producer-stream"))
+
     class Net(nn.Module):
         def __init__(self):
             super().__init__()
@@ -250,9 +258,8 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
     ddp = tdp.NaiveDDP(wrapped, sync=False, gradient_as_bucket_view=True, num_grad_acc_iter=2)
     red = ddp.reducer
     for name, p in red.params.items():         # what the reducer does itself on CUDA
-        if p.dim() == 2:
-            p._tdp_main_grad = red.param_bucket[name].views[name]
-            p._tdp_grad_fresh = True
+        p._tdp_main_grad = red.param_bucket[name].views[name]      # weights AND biases
+        p._tdp_grad_fresh = True
     ready_calls = []
     orig_ready = red._on_grad_ready
     monkeypatch.setattr(red, "_on_grad_ready", lambda n, p: (ready_calls.append(n), orig_ready(n, p))[1])
@@ -273,6 +280,10 @@ def test_ddp_direct_weight_gradient_control_flow(monkeypatch):
             assert q.grad.data_ptr() == red.param_bucket[n].views[n].data_ptr(), n
             assert torch.allclose(q.grad.float(), p.grad.float(), rtol=2e-2, atol=1e-3), n
         assert all(p._tdp_grad_fresh for p in wrapped.parameters() if hasattr(p, "_tdp_grad_fresh"))
+        # the hook hands the producing stream of every directly written gradient to its bucket
+        # (on CUDA _reduce_bucket orders the comm stream behind it) and clears it on the parameter
+        assert all(getattr(p, "_tdp_grad_stream", None) is None for p in wrapped.parameters())
+        assert all("producer-stream" in b.producer_streams for b in red.buckets)
 
 
 def test_step_watchdog_fires_and_recovers():
