@@ -13,4 +13,4 @@ class GEGLU(nn.Module):
 
 dev = "cuda" if torch.cuda.is_available() else "cpu"
 model = nn.Sequential(GEGLU(512, 2048), nn.Linear(2048, 512), nn.LayerNorm(512)).to(dev)
-tdp.get_model_profile(model, args=(torch.randn(64, 128, 512, device=dev),), sort=True, max_depth=2)
+tdp.get_model_profile(model, args=(torch.randn(64, 128, 512, device=dev),), sort=False, max_depth=2)

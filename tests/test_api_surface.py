@@ -1,0 +1,287 @@
+"""Drop-in check: every public name, import path and call signature a user of the reference
+package relies on exists here (reference torchdistpackage/__init__.py:1-24,
+parallel/__init__.py:1-7 and the per-module definitions).
+
+The lists below are what the reference *defines*; the test does not import the reference.  When
+the unmodified reference is installed under ``baseline/_ref`` (the benchmark's reference arm) a
+second test parses its sources and checks that nothing public was added there that is missing
+here."""
+import ast
+import importlib
+import inspect
+import os
+
+import pytest
+import torch
+
+PKG = "torchdistpackage_b200"
+
+ROOT_NAMES = [
+    "NaiveDDP", "NaiveDdp", "moe_dp_iter_step", "create_moe_dp_hooks", "Bf16ZeroOptimizer",
+    "setup_distributed", "tpc", "torch_parallel_context", "test_comm", "is_using_pp",
+    "setup_node_groups", "ShardedEMA", "fix_rand", "partition_params", "report_prof",
+    "register_profile_hooks", "get_model_profile", "replace_all_module", "replace_linear_by_bnb",
+    "replace_linear_by_bminf",
+]
+
+PARALLEL_NAMES = [
+    "forward_backward", "forward_eval", "partition_uniform", "flatten_model", "ParallelBlock",
+    "Block", "Attention", "TpAttention", "Mlp", "TpMlp",
+    # tp_utils.* (star import in the reference)
+    "get_tp_group", "set_tp_group", "TpLinear", "ColParallelLinear", "RowParallelLinear",
+    "gather_from_sequence_parallel_region", "reduce_scatter_to_sequence_parallel_region",
+    "maybe_gather_from_sequence_parallel", "maybe_split_into_sequence_parallel",
+    "set_sequence_parallel_attr", "is_squence_parallel_tensor",
+]
+
+# module path (below the package root) -> names defined there by the reference
+MODULE_NAMES = {
+    "dist.launch_from_slurm": ["setup_distributed", "find_free_port"],
+    "dist.process_topo": ["ProcessTopology", "torch_parallel_context", "test_comm", "is_using_pp",
+                          "gen_groups", "gen_inner_ranks"],
+    "dist.node_group": ["setup_node_groups"],
+    "dist.sharded_ema": ["ShardedEMA"],
+    "dist.model_parallel_ckpt": ["get_mp_ckpt_suffix"],
+    "dist.utils": ["cu_prof_start", "cu_prof_stop", "nvtx_decorator", "NVTXContext",
+                   "_has_inf_or_nan", "disable_non_master_print"],
+    "dist.py_comm_test": ["test_collection", "test_all2all_balanced", "mode_2_frac"],
+    "utils": ["fix_rand", "partition_params"],
+    "ddp.naive_ddp": ["NaiveDDP", "MoEDP", "GradBucket", "create_moe_dp_hooks", "moe_dp_iter_step"],
+    "ddp.zero_optim": ["Bf16ZeroOptimizer", "partition_params"],
+    "parallel.pipeline_parallel.pipeline_sched": ["forward_backward", "forward_eval"],
+    "parallel.pipeline_parallel.comm": [
+        "send_obj_meta", "recv_obj_meta", "split_tensor_into_1d_equal_chunks",
+        "gather_split_1d_tensor", "_communicate", "recv_forward", "recv_backward", "send_forward",
+        "send_backward", "send_forward_recv_backward", "send_backward_recv_forward",
+        "send_forward_recv_forward", "send_backward_recv_backward",
+        "send_forward_backward_recv_forward_backward"],
+    "parallel.pipeline_parallel.pipeline_helper": [
+        "partition_uniform", "partition_balanced", "flatten_sequence", "CallableModule",
+        "flatten_model", "flat_and_partition"],
+    "parallel.pipeline_parallel.clip_grad_parallel": ["clip_grad_norm_", "NativeScalerPP"],
+    "parallel.tensor_parallel.tp_utils": [
+        "get_tp_group", "set_tp_group", "get_tensor_model_parallel_world_size",
+        "set_sequence_parallel_attr", "is_squence_parallel_tensor",
+        "_ReduceFromModelParallelRegion", "_reduce_scatter_along_first_dim",
+        "_gather_along_first_dim", "_split_along_first_dim",
+        "_ReduceScatterToSequenceParallelRegion", "_GatherFromSequenceParallelRegion",
+        "gather_from_sequence_parallel_region", "reduce_scatter_to_sequence_parallel_region",
+        "maybe_gather_from_sequence_parallel", "maybe_split_into_sequence_parallel",
+        "TpLinear", "ColParallelLinear", "RowParallelLinear"],
+    "parallel.tensor_parallel.attn": ["Attention", "TpAttention", "_split_heads"],
+    "parallel.tensor_parallel.mlp": ["Mlp", "TpMlp"],
+    "parallel.tensor_parallel.transformer": ["Block", "ParallelBlock", "Transformer"],
+    "tools.module_profiler": ["get_dt_size", "count_tensor_size", "output_same_as_input", "get_level",
+                              "register_profile_hooks", "divide_by_layer", "sort_mem_time_ratio",
+                              "report_prof", "get_model_profile"],
+    "tools.debug_nan": ["check_tensor_inf_nan", "check_tensors", "check_model_params",
+                        "fwd_hook_wrapper", "bwd_hook_wrapper"],
+    "tools.module_replace": ["replace_all_module"],
+    "tools.bnb_fc": ["replace_linear_by_bnb", "if_replace_linear", "get_new_module"],
+    "tools.bminf_int8": ["replace_linear_by_bminf"],
+    "tools.slurm_job_monitor": ["monitor_job"],
+}
+
+# class -> public methods / properties of the reference
+CLASS_MEMBERS = {
+    ("ddp.naive_ddp", "NaiveDDP"): ["forward", "reduce_gradients", "broadcast_params", "sync_comm",
+                                    "reduce_dispatch", "_get_group"],
+    ("ddp.naive_ddp", "MoEDP"): ["reduce_gradients", "broadcast_params", "reduce_dispatch"],
+    ("ddp.naive_ddp", "GradBucket"): ["get_aligned_size", "grad_ready", "grad_reset", "can_fit", "push"],
+    ("ddp.zero_optim", "Bf16ZeroOptimizer"): ["step", "zero_grad", "state", "param_groups"],
+    ("dist.sharded_ema", "ShardedEMA"): ["update", "state_dict_cpu", "verify_with_gt"],
+    ("dist.process_topo", "ProcessTopology"): [
+        "setup_process_groups", "build_moe_groups", "get_group", "get_group_rank",
+        "get_ranks_in_group", "get_group_size", "get_tp_rank", "get_pp_rank", "get_dp_rank",
+        "get_mp_rank", "get_tp_size", "get_pp_size", "get_dp_size", "get_mp_size",
+        "is_first_in_group", "is_last_in_group", "is_first_in_tensor_group",
+        "is_last_in_tensor_group", "is_first_in_pipeline_group", "is_last_in_pipeline_group",
+        "is_first_in_data_group", "is_last_in_data_group", "is_first_in_model_group",
+        "is_last_in_model_group", "get_prev_global_rank", "get_next_global_rank", "is_mode_inited",
+        "all_dp_ranks", "all_ranks", "is_first_group"],
+    ("parallel.tensor_parallel.tp_utils", "ColParallelLinear"): [
+        "forward", "init_weight_from_full", "init_weight_from_full_attn"],
+    ("parallel.tensor_parallel.tp_utils", "RowParallelLinear"): ["forward", "init_weight_from_full"],
+    ("parallel.tensor_parallel.transformer", "ParallelBlock"): ["forward", "init_from_full"],
+    ("parallel.pipeline_parallel.clip_grad_parallel", "NativeScalerPP"): [
+        "__call__", "state_dict", "load_state_dict", "state_dict_key"],
+    ("dist.utils", "NVTXContext"): ["__enter__", "__exit__"],
+}
+
+# callable -> leading parameter names (and the defaults that matter) of the reference signature
+SIGNATURES = {
+    ("ddp.naive_ddp", "NaiveDDP"): (["module", "sync", "bucket_cap_mb", "gradient_as_bucket_view",
+                                     "process_group", "dp_rank0", "reduce_op"],
+                                    dict(sync=False, bucket_cap_mb=25, gradient_as_bucket_view=False,
+                                         process_group=None, dp_rank0=0, reduce_op="avg")),
+    ("ddp.naive_ddp", "create_moe_dp_hooks"): (["params", "moe_dp_group", "moe_dp_rank0", "overlap_comm",
+                                                "reduce_op", "sync", "num_grad_acc_iter"], {}),
+    ("ddp.zero_optim", "Bf16ZeroOptimizer"): (["optim", "dp_group", "bf16_master_weights", "overlap_comm",
+                                               "stage", "bucket_size", "bucketize"],
+                                              dict(dp_group=None, bf16_master_weights=False,
+                                                   overlap_comm=False, stage=2, bucket_size=5e8,
+                                                   bucketize=True)),
+    ("parallel.pipeline_parallel.pipeline_sched", "forward_backward"): (
+        ["optimizer", "fwd_fn", "bwd_fn", "inputs", "num_microbatches", "forward_only", "dtype",
+         "scatter_gather_tensors"],
+        dict(num_microbatches=1, forward_only=False, dtype=torch.bfloat16, scatter_gather_tensors=False)),
+    ("parallel.pipeline_parallel.pipeline_sched", "forward_eval"): (["fwd_fn", "inputs", "dtype"], {}),
+    ("dist.sharded_ema", "ShardedEMA"): (["model", "group"], dict(group=None)),
+    ("dist.sharded_ema", "ShardedEMA.update"): (["self", "model", "decay", "only_trainable"],
+                                                dict(decay=0.9999, only_trainable=True)),
+    ("parallel.tensor_parallel.mlp", "TpMlp"): (["in_features", "hidden_features", "out_features",
+                                                 "act_layer", "tp_group", "bias", "drop",
+                                                 "sequence_parallel"], dict(sequence_parallel=False)),
+    ("parallel.tensor_parallel.attn", "TpAttention"): (["dim", "num_heads", "qkv_bias", "attn_drop",
+                                                        "proj_drop", "tp_group", "sequence_parallel"],
+                                                       dict(num_heads=8, qkv_bias=False)),
+    ("parallel.tensor_parallel.transformer", "Transformer"): (
+        ["dim", "mlp_ratio", "num_heads", "depth", "tensor_parallel", "sequence_parallel"],
+        dict(mlp_ratio=4, num_heads=8, depth=12, tensor_parallel=True, sequence_parallel=True)),
+    ("dist.launch_from_slurm", "setup_distributed"): (["backend", "port"], dict(backend="nccl", port=None)),
+    ("dist.node_group", "setup_node_groups"): (["num_per_node"], dict(num_per_node=8)),
+    ("utils", "partition_params"): (["model", "num_partitions", "return_dict"], dict(return_dict=False)),
+    ("utils", "fix_rand"): (["rank"], dict(rank=0)),
+    ("dist.py_comm_test", "test_collection"): (["ele_num_total", "mode", "group"],
+                                               dict(mode="all_reduce", group=None)),
+    ("dist.py_comm_test", "test_all2all_balanced"): (["ele_num", "group"], dict(group=None)),
+    ("tools.module_profiler", "get_model_profile"): (["model", "args", "kwargs", "sort", "topn",
+                                                      "max_depth", "min_mem"],
+                                                     dict(sort=True, topn=20, max_depth=5, min_mem=50)),
+    ("tools.module_profiler", "report_prof"): (["infos", "topn", "max_depth", "min_mem", "sort"],
+                                               dict(topn=20, max_depth=5, min_mem=50, sort=True)),
+    ("tools.module_profiler", "register_profile_hooks"): (["model", "infos"], {}),
+    ("tools.module_replace", "replace_all_module"): (["model", "if_replace_hook", "get_new_module"], {}),
+    ("tools.debug_nan", "fwd_hook_wrapper"): (["module_name"], {}),
+    ("tools.debug_nan", "bwd_hook_wrapper"): (["module_name"], {}),
+    ("parallel.pipeline_parallel.clip_grad_parallel", "clip_grad_norm_"): (
+        ["parameters", "max_norm", "norm_type", "error_if_nonfinite", "foreach"],
+        dict(norm_type=2.0, error_if_nonfinite=False)),
+    ("parallel.pipeline_parallel.clip_grad_parallel", "NativeScalerPP.__call__"): (
+        ["self", "loss", "optimizer", "clip_grad", "clip_mode", "parameters", "create_graph",
+         "need_update"], dict(clip_grad=None, clip_mode="norm", need_update=True)),
+    ("parallel.pipeline_parallel.pipeline_helper", "partition_uniform"): (["flat_sequence", "extra_len"],
+                                                                          dict(extra_len=0)),
+    ("parallel.pipeline_parallel.pipeline_helper", "flatten_model"): (["model", "layer_list", "return_list"],
+                                                                      dict(return_list=False)),
+}
+
+
+def _mod(path: str):
+    return importlib.import_module(f"{PKG}.{path}")
+
+
+def _resolve(path: str, qual: str):
+    obj = _mod(path)
+    for part in qual.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def test_root_and_parallel_exports():
+    tdp = importlib.import_module(PKG)
+    missing = [n for n in ROOT_NAMES if not hasattr(tdp, n)]
+    assert not missing, missing
+    par = _mod("parallel")
+    missing = [n for n in PARALLEL_NAMES if not hasattr(par, n)]
+    assert not missing, missing
+    assert tdp.tpc is tdp.torch_parallel_context            # one topology object
+    assert tdp.NaiveDdp is tdp.NaiveDDP
+
+
+def test_module_paths_and_names():
+    missing = []
+    for path, names in MODULE_NAMES.items():
+        mod = _mod(path)
+        missing += [f"{path}.{n}" for n in names if not hasattr(mod, n)]
+    for (path, cls), members in CLASS_MEMBERS.items():
+        c = getattr(_mod(path), cls)
+        missing += [f"{path}.{cls}.{m}" for m in members if not hasattr(c, m)]
+    assert not missing, missing
+
+
+@pytest.mark.parametrize("key", sorted(SIGNATURES), ids=lambda k: f"{k[0]}.{k[1]}")
+def test_signatures_accept_reference_calls(key):
+    names, defaults = SIGNATURES[key]
+    params = inspect.signature(_resolve(*key)).parameters
+    ours = [n for n, p in params.items()
+            if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+    assert ours[:len(names)] == names, (ours, names)
+    for n, v in defaults.items():
+        assert params[n].default == v, (n, params[n].default, v)
+
+
+def test_reference_conventions():
+    """Behavioural details of small helpers a switched-over script depends on."""
+    from torchdistpackage_b200.dist.utils import nvtx_decorator, NVTXContext
+    from torchdistpackage_b200.tools.debug_nan import check_tensors, check_tensor_inf_nan
+    from torchdistpackage_b200.dist.process_topo import gen_groups, gen_inner_ranks, compute_layout
+    from torchdistpackage_b200.dist.py_comm_test import mode_2_frac
+
+    @nvtx_decorator                      # bare, as the reference is used
+    def f(x):
+        return x + 1
+
+    @nvtx_decorator("named")
+    def g(x):
+        return x + 2
+    assert f(1) == 2 and g(1) == 3 and f.__name__ == "f"
+    with NVTXContext("ctx", record_time=False):
+        pass
+    assert check_tensors(torch.ones(2)) and check_tensor_inf_nan(torch.ones(2))     # True == clean
+    assert not check_tensors([torch.tensor([float("nan")])])
+    assert gen_inner_ranks(8, 4) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    seen = []
+    lists = gen_groups(16, 2, [2], seen.append)                  # pipe=2 above tensor=2
+    assert lists == seen == compute_layout(16, [("data", 4), ("pipe", 2), ("tensor", 2)])["pipe"]
+    assert gen_groups(16, 4, [2, 2], None)[0] == [0, 4, 8, 12]
+    assert mode_2_frac["all_reduce"] == 2 and mode_2_frac["all_gather"] == 1
+
+
+def _public_defs(tree):
+    out = []
+    for node in tree.body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and not node.name.startswith("_"):
+            out.append(node.name)
+    return out
+
+
+# reference names deliberately not carried over (internals of its implementation strategy)
+_NOT_CARRIED = {
+    "dist.process_topo": {"SingletonMeta"},                       # ProcessTopology.__new__ instead
+    "ddp.zero_optim": {"Bucket"},                                 # element-wise sharding: _ZBucket
+    "parallel.pipeline_parallel.comm": {"get_current_device", "send_meta_helper", "recv_meta_helper",
+                                        "create_recv_buffer_with_shapes", "process_object_to_send",
+                                        "filling_ops_queue"},     # one packed meta message instead
+    "tools.module_profiler": {"fwd_pre_hook_wrapper", "fwd_hook_wrapper"},   # closures in register_*
+    "tools.bminf_int8": {"if_replace_linear", "get_new_module"},
+}
+
+
+def test_against_installed_reference_sources():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "baseline", "_ref", "torchdistpackage")
+    if not os.path.isdir(root):
+        pytest.skip("reference arm not installed (baseline/_ref)")
+    missing = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith(".py") or f == "__init__.py":
+                continue
+            full = os.path.join(dirpath, f)
+            path = os.path.relpath(full, root)[:-3].replace(os.sep, ".")
+            try:
+                mod = _mod(path)
+            except ImportError:
+                missing.append(path)
+                continue
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                tree = ast.parse(open(full).read())
+            for name in _public_defs(tree):
+                if name in _NOT_CARRIED.get(path, ()):
+                    continue
+                if not hasattr(mod, name):
+                    missing.append(f"{path}.{name}")
+    assert not missing, missing

@@ -46,6 +46,14 @@ def _w_topology(rank, world):
     assert tdp.setup_node_groups(2) is not None       # 4 ranks, 2 per "node"
     assert tdp.setup_node_groups(8) is None
     assert tdp.get_mp_ckpt_suffix() == f"_tp_{rank % 2}.pth"
+    # the collective micro-benchmark, every mode, world group and a sub-group (on gloo the NCCL arm)
+    from torchdistpackage_b200.dist.py_comm_test import test_collection, test_all2all_balanced
+    for mode in ("all_reduce", "all_gather", "reduce_scatter"):
+        bw, sec = test_collection(1 << 14, mode, verbose=False, warmup=1, iters=2)   # reference-style unpack
+        assert bw >= 0 and sec > 0
+    res = test_collection(1 << 14, "all_reduce", tpc.get_group("tensor"), verbose=False, warmup=1, iters=2)
+    assert res["world"] == 2 and res["bytes"] == (1 << 14) * 4 and res["busbw_gbs"] > 0
+    assert test_all2all_balanced(1 << 12, verbose=False, warmup=1, iters=2)["mode"] == "all_to_all"
 
 
 def test_topology_and_comm():

@@ -66,15 +66,27 @@ def test_partition_params_and_fix_rand():
 
 def test_module_profiler_and_replace(capsys):
     model = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Sequential(nn.Linear(16, 16), nn.Linear(16, 4)))
-    prof = tdp.get_model_profile(model, args=(torch.randn(2, 8),), sort=True, max_depth=2)
+    prof = tdp.get_model_profile(model, args=(torch.randn(2, 8),), sort=False, max_depth=2)
     out = capsys.readouterr().out
-    assert "level 0" in out and "level 1" in out and 1 in prof and len(prof[1]) == 3
-    handles = tdp.register_profile_hooks(model)
-    model(torch.randn(2, 8))
-    rep = tdp.report_prof(topn=2)
-    assert len(rep[1]) == 2
+    # container indices do not open a level: "2.0" / "2.1" report next to "0", "1", "2"
+    assert "level: 0" in out and "level: 1" in out and 1 in prof and len(prof[1]) == 5
+    from torchdistpackage_b200.tools.module_profiler import get_level, count_tensor_size, divide_by_layer
+    assert [get_level(n) for n in ("root", "blocks", "blocks.3", "blocks.12.attn", "blocks.3.attn.qkv")] \
+        == [0, 1, 1, 2, 3]
+    assert count_tensor_size([torch.zeros(4, dtype=torch.int8), (torch.zeros(2, 2),)]) == 4 + 16
+    assert set(divide_by_layer()) == {0, 1}
+    # the reference's calling convention: infos = register(model); run; report_prof(infos, ...)
+    infos = tdp.register_profile_hooks(model, backward=True)
+    model(torch.randn(2, 8, requires_grad=True)).sum().backward()
+    rep = tdp.report_prof(infos, topn=2, min_mem=0)
+    assert len(rep[1]) == 2 and infos["root"]["fwd_time"] > 0 and infos["2.1"]["bwd_time"] > 0
+    assert len(tdp.report_prof(infos)[1]) == 0            # default filter: >= 50 MB per module
     from torchdistpackage_b200.tools import remove_profile_hooks
     remove_profile_hooks()
+    assert not infos.handles
+    calls = infos["root"]["calls"]
+    model(torch.randn(2, 8))
+    assert infos["root"]["calls"] == calls                # hooks are gone
     tdp.replace_all_module(model, lambda m: isinstance(m, nn.ReLU), lambda m: nn.GELU())
     assert isinstance(model[1], nn.GELU)
     from torchdistpackage_b200.tools.module_profiler import get_dt_size
@@ -88,8 +100,15 @@ def test_nan_hooks():
     model(torch.randn(2, 4))
     with pytest.raises(FloatingPointError):
         model(torch.full((2, 4), float("nan")))
+    # reference polarity: True == clean
+    assert check_model_params(model)
+    assert not check_tensors([torch.tensor([1.0, float("inf")])], "x")
+    assert check_tensors((torch.ones(2), [torch.zeros(1)], {"a": torch.ones(1)}))
+    from torchdistpackage_b200.tools.debug_nan import check_tensor_inf_nan
+    assert check_tensor_inf_nan(torch.ones(3)) and not check_tensor_inf_nan(torch.tensor([float("nan")]))
+    with torch.no_grad():
+        model[0].weight[0, 0] = float("nan")
     assert not check_model_params(model)
-    assert check_tensors([torch.tensor([1.0, float("inf")])], "x")
 
 
 def test_dist_utils_and_comm_formula():

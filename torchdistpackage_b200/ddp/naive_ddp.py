@@ -66,6 +66,11 @@ class GradBucket:
         self.producer_streams = set()
 
     # ---- layout
+    def get_aligned_size(self, tensor: torch.Tensor) -> int:
+        """Elements ``tensor`` occupies in the bucket including the alignment padding behind it
+        (reference helper of this name, naive_ddp.py:456-461)."""
+        return align_up(tensor.numel(), self.elem_align())
+
     def elem_align(self) -> int:
         return max(1, _ALIGN_BYTES // self.buffer.element_size())
 
@@ -472,6 +477,13 @@ class NaiveDDP(torch.nn.Module):
         if self.reducer.on_cuda:
             self.reducer.comm_stream.synchronize()
 
+    def reduce_dispatch(self, name: str, p: torch.nn.Parameter) -> None:
+        """What the gradient hook of parameter ``name`` runs (reference: naive_ddp.py:129-171):
+        marks the gradient final for this micro-batch and launches the bucket's reduction once
+        all of its gradients are.  Exposed for custom schedules that produce a gradient outside
+        autograd and for subclasses; the hooks call the reducer directly."""
+        self.reducer._on_grad_ready(name, p)
+
     def set_num_grad_acc_iter(self, n: int) -> None:
         self.reducer.num_grad_acc_iter = max(int(n), 1)
 
@@ -525,6 +537,17 @@ class MoEDP:
 
     def reduce_gradients(self) -> None:
         self.reducer.finalize()
+
+    def broadcast_params(self) -> None:
+        """Re-send the expert parameters from ``moe_dp_rank0`` (done once by the constructor)."""
+        _GradReducer.broadcast_tensors([p.data for p in self.params.values()], self.rank0,
+                                       self.group)
+
+    def reduce_dispatch(self, name: str, p: torch.nn.Parameter) -> None:
+        self.reducer._on_grad_ready(name, p)
+
+    def remove_hooks(self) -> None:
+        self.reducer.remove_hooks()
 
 
 moe_dp_mod: Optional[MoEDP] = None

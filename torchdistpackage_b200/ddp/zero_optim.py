@@ -51,6 +51,24 @@ from ..ops.symm import get_symm_group
 from ..utils.flat import align_up
 
 
+def partition_params(params, num_partitions: int, numel_per_partition: Optional[int] = None):
+    """Whole-tensor partition of ``params`` into ``num_partitions`` contiguous lists -- the
+    reference's ZeRO sharding rule (ddp/zero_optim.py:19-41: a shard is closed once it exceeds
+    ``numel_per_partition`` elements).  Kept as a utility: this optimizer shards *element-wise*
+    (every rank owns 1/N of every bucket), which balances perfectly whatever the tensor sizes."""
+    params = list(params)
+    parts: List[list] = [[] for _ in range(num_partitions)]
+    if numel_per_partition is None:
+        numel_per_partition = sum(p.numel() for p in params) // max(num_partitions, 1)
+    cur, acc = 0, 0
+    for p in params:
+        parts[cur].append(p)
+        acc += p.numel()
+        if acc > numel_per_partition and cur < num_partitions - 1:
+            cur, acc = cur + 1, 0
+    return parts
+
+
 class _ZBucket:
     """A contiguous range of the flat buffers: [start, start + numel), numel = world * slice."""
 

@@ -52,6 +52,22 @@ def compute_axis_layout(world_size: int, size: int, inner_sizes: Sequence[int]) 
     return groups
 
 
+def gen_inner_ranks(world_size: int, group_size: int) -> List[List[int]]:
+    """Consecutive rank lists of an innermost axis (reference helper, process_topo.py:28-30)."""
+    return compute_axis_layout(world_size, group_size, ())
+
+
+def gen_groups(world_size: int, group_size: int, strides=None, hook=None) -> List[List[int]]:
+    """Reference-style front end of :func:`compute_axis_layout` (process_topo.py:32-51): rank
+    lists of an axis of extent ``group_size`` whose inner axes have the extents ``strides``;
+    ``hook`` (if given) is called once per rank list, in enumeration order."""
+    lists = compute_axis_layout(world_size, group_size, tuple(strides or ()))
+    if hook is not None:
+        for ranks in lists:
+            hook(ranks)
+    return lists
+
+
 def compute_layout(world_size: int, config: AxisConfig) -> Dict[str, List[List[int]]]:
     """All rank lists for a ``[(axis, size), ...]`` config (outermost first) incl. ``'model'``."""
     names = [c[0] for c in config]

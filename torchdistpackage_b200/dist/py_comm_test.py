@@ -21,12 +21,35 @@ import torch.distributed as dist
 
 from .launch import setup_distributed
 
+# bus bandwidth = algorithm bandwidth x fraction x (n-1)/n  (the NCCL-tests convention the
+# reference uses, py_comm_test.py:10-17)
 _FRAC = {"all_reduce": 2.0, "all_gather": 1.0, "reduce_scatter": 1.0, "all_to_all": 1.0}
+mode_2_frac = _FRAC
 
 
 def bus_bandwidth_gbs(mode: str, total_bytes: int, seconds: float, n: int) -> float:
     algbw = total_bytes / max(seconds, 1e-12) / 1e9
     return algbw * _FRAC[mode] * (n - 1) / max(n, 1)
+
+
+class CommResult(tuple):
+    """What :func:`test_collection` returns.  Unpacks like the reference's return value --
+    ``bw, time_avg = test_collection(...)`` = (bus bandwidth in GB/s, seconds per call),
+    py_comm_test.py:48-57 -- and carries the full record: ``res["ms"]``, ``res["algbw_gbs"]``,
+    ``res["busbw_gbs"]``, ``res["bytes"]``, ``res["world"]``, ... or ``res.info`` as a dict."""
+
+    def __new__(cls, info: dict):
+        obj = super().__new__(cls, (round(info["busbw_gbs"], 3), info["ms"] * 1e-3))
+        obj.info = dict(info)
+        return obj
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.info[key]
+        return super().__getitem__(key)
+
+    def keys(self):
+        return self.info.keys()
 
 
 def _timed(fn, warmup: int, iters: int, device) -> float:
@@ -53,10 +76,12 @@ def _timed(fn, warmup: int, iters: int, device) -> float:
     return float(t.item())
 
 
-def test_collection(numel_total: int, mode: str = "all_reduce", group=None, impl: str = "nccl",
-                    dtype=torch.bfloat16, warmup: int = 3, iters: int = 10, verbose: bool = True):
-    """Measure one collective.  ``numel_total`` = elements of the *full* (gathered / reduced)
-    tensor.  Returns a dict with ms, algbw and busbw (GB/s)."""
+def test_collection(ele_num_total: int, mode: str = "all_reduce", group=None, impl: str = "nccl",
+                    dtype=torch.bfloat16, warmup: int = 3, iters: int = 10,
+                    verbose: bool = True) -> CommResult:
+    """Measure one collective.  ``ele_num_total`` = elements of the *full* (gathered / reduced)
+    tensor.  Returns a :class:`CommResult` (``(busbw GB/s, seconds)`` + the full record)."""
+    numel_total = int(ele_num_total)
     world = dist.get_world_size(group)
     cuda = torch.cuda.is_available() and dist.get_backend(group) == "nccl"
     device = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
@@ -111,11 +136,12 @@ def test_collection(numel_total: int, mode: str = "all_reduce", group=None, impl
                busbw_gbs=bus_bandwidth_gbs(mode, total_bytes, sec, world))
     if verbose and dist.get_rank() == 0:
         print(json.dumps(res), flush=True)
-    return res
+    return CommResult(res)
 
 
-def test_all2all_balanced(numel_total: int, group=None, **kw):
-    return test_collection(numel_total, "all_to_all", group, **kw)
+def test_all2all_balanced(ele_num: int, group=None, **kw):
+    """Balanced ``all_to_all_single`` of ``ele_num`` elements per rank (reference: :60-78)."""
+    return test_collection(ele_num, "all_to_all", group, **kw)
 
 
 def main():

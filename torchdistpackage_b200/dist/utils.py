@@ -37,7 +37,13 @@ def _nvtx_pop() -> None:
         torch.cuda.nvtx.range_pop()
 
 
-def nvtx_decorator(name: str = None):
+def nvtx_decorator(func=None, name: str = None):
+    """NVTX range around every call of the decorated function.  Usable bare, as in the reference
+    (``@nvtx_decorator``, dist/utils.py:35-45: the range is named after the function), or with a
+    label (``@nvtx_decorator("fwd")`` / ``@nvtx_decorator(name="fwd")``)."""
+    if isinstance(func, str):
+        func, name = None, func
+
     def deco(fn):
         label = name or fn.__qualname__
 
@@ -49,14 +55,15 @@ def nvtx_decorator(name: str = None):
             finally:
                 _nvtx_pop()
         return wrapped
-    return deco
+    return deco(func) if callable(func) else deco
 
 
 class NVTXContext:
     """``with NVTXContext('fwd', record_time=True) as c: ...`` -> ``c.elapsed_ms``"""
 
-    def __init__(self, name: str, record_time: bool = False, enabled: bool = True):
-        self.name, self.record_time, self.enabled = name, record_time, enabled
+    def __init__(self, context_name: str, record_time: bool = False, enabled: bool = True):
+        self.name = self.context_name = context_name
+        self.record_time, self.enabled = record_time, enabled
         self.elapsed_ms = None
 
     def __enter__(self):

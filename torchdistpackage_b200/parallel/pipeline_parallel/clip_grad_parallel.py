@@ -134,12 +134,19 @@ class NativeScalerPP:
                 if tpc.is_mode_inited(mode):
                     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=tpc.get_group(mode))
 
-    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False,
-                 update_grad=True, backward: bool = True):
+    def __call__(self, loss, optimizer, clip_grad=None, clip_mode: str = "norm", parameters=None,
+                 create_graph=False, need_update=True, update_grad=None, backward: bool = True):
+        """Positional layout of the reference (:105-114): ``(loss, optimizer, clip_grad,
+        clip_mode, parameters, create_graph, need_update)``.  ``update_grad`` is timm's spelling of
+        ``need_update``; ``backward=False`` when the pipeline scheduler already ran backward."""
+        if clip_mode != "norm":
+            raise NotImplementedError("only gradient-norm clipping is model-parallel aware")
+        if update_grad is not None:
+            need_update = update_grad
         if backward:
             self._scaler.scale(loss).backward(create_graph=create_graph)
         norm = None
-        if update_grad:
+        if need_update:
             self._scaler.unscale_(optimizer)
             self._sync_found_inf(optimizer)
             if clip_grad is not None and parameters is not None:

@@ -47,14 +47,13 @@ def greedy_partition_sizes(numels: List[int], num_partitions: int) -> List[int]:
     return owners
 
 
-def partition_params(model_or_named: Union[torch.nn.Module, Iterable[Tuple[str, torch.Tensor]]],
+def partition_params(model: Union[torch.nn.Module, Iterable[Tuple[str, torch.Tensor]]],
                      num_partitions: int, return_dict: bool = False):
     """Greedy numel-balanced partition of ``named_parameters`` into ``num_partitions`` shards.
 
     Returns a list (length ``num_partitions``) of lists of parameters, or of ``{name: param}``
     dicts when ``return_dict`` is set."""
-    named = list(model_or_named.named_parameters()) if isinstance(model_or_named, torch.nn.Module) \
-        else list(model_or_named)
+    named = list(model.named_parameters()) if isinstance(model, torch.nn.Module) else list(model)
     owners = greedy_partition_sizes([p.numel() for _, p in named], num_partitions)
     parts: List = [dict() if return_dict else list() for _ in range(num_partitions)]
     for (name, p), o in zip(named, owners):
