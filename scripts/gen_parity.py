@@ -226,6 +226,7 @@ SASS listings per kernel family: `profiles/sass/`; ncu summaries: `profiles/ncu/
 | 5.8 B200-native comm backend | `csrc/coll/collectives.cu`, `csrc/symm/symm_vmm.cpp`, `ops/symm.py`, `DESIGN.md` 3 |
 """
 
-with open(os.path.join(ROOT, "PARITY.md"), "w") as f:
-    f.write(doc)
-print("wrote PARITY.md,", doc.count("\n"), "lines")
+if __name__ == "__main__":
+    with open(os.path.join(ROOT, "PARITY.md"), "w") as f:
+        f.write(doc)
+    print("wrote PARITY.md,", doc.count("\n"), "lines")
