@@ -345,12 +345,39 @@ OTHER_CONFIGS = [
 ]
 
 
+def _agree_to_run(rank: int, tag: str, go: bool, wait_s: float = 90.0) -> bool:
+    """All ranks of this node take rank 0's decision (the process group is already gone, and a
+    rank that starts a side run alone would sit in its rendezvous until the timeout): rank 0
+    publishes it as a file, the others wait for the file."""
+    path = os.path.join("/tmp", f"tdp_bench_{tag}")
+    if rank == 0:
+        tmp = path + ".tmp"
+        with open(tmp, "w") as f:
+            f.write("go" if go else "skip")
+        os.replace(tmp, path)
+        return go
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < wait_s:
+        try:
+            with open(path) as f:
+                return f.read().strip() == "go"
+        except OSError:
+            time.sleep(0.05)
+    return False
+
+
 def run_other_configs(rank, world):
     """BASELINE configs #3 / #4 / #5, both arms, each as a fresh set of ``world`` processes (this
     rank spawns its counterpart with the same RANK / LOCAL_RANK on a new rendezvous port), timed by
     the scripts themselves (CUDA events, max over ranks) -- outside the headline timed region.
-    Returns {name: {ours_ms, reference_ms, ratio, ...}} on rank 0."""
+    The whole section has a wall-clock budget (``TDP_BENCH_OTHER_BUDGET_S``, default 420 s; a
+    healthy side run takes about half a minute): once it is spent the remaining runs are
+    skipped and reported as such, so a stuck side config cannot hold the headline line back
+    for long.  Returns {name: {ours_ms, reference_ms, ratio, ...}} on rank 0."""
     base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    budget = float(os.environ.get("TDP_BENCH_OTHER_BUDGET_S", "420"))
+    t_begin = time.perf_counter()
+    tag = f"{base_port}_{os.getppid()}"      # the launcher's pid: same on every rank, new per launch
     out = {}
     idx = 0
     for name, script, title in OTHER_CONFIGS:
@@ -359,6 +386,11 @@ def run_other_configs(rank, world):
         rec = {"config": title}
         for impl in ("reference", "ours"):
             idx += 1
+            left = budget - (time.perf_counter() - t_begin)
+            if not _agree_to_run(rank, f"{tag}_{idx}", left > 30.0):
+                if rank == 0:
+                    rec[impl + "_error"] = "skipped: time budget of the side configs spent"
+                continue
             env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC")}
             env["MASTER_PORT"] = str(base_port + 100 + idx)
             env["MASTER_ADDR"] = "127.0.0.1"
@@ -366,7 +398,7 @@ def run_other_configs(rank, world):
             try:
                 cp = subprocess.run([sys.executable, os.path.join(ROOT, script), "--impl", impl],
                                     env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                                    text=True, timeout=240)
+                                    text=True, timeout=180)
                 for ln in cp.stdout.splitlines():
                     if ln.startswith("{"):
                         res = json.loads(ln)
@@ -382,6 +414,13 @@ def run_other_configs(rank, world):
         if "ours_ms_per_step" in rec and "reference_ms_per_step" in rec:
             rec["ratio"] = rec["reference_ms_per_step"] / rec["ours_ms_per_step"]
         out[name] = rec
+    if rank == 0:
+        out["wall_s"] = round(time.perf_counter() - t_begin, 1)
+        for i in range(1, idx + 1):
+            try:
+                os.remove(os.path.join("/tmp", f"tdp_bench_{tag}_{i}"))
+            except OSError:
+                pass
     return out
 
 
