@@ -217,7 +217,7 @@ SASS listings per kernel family: `profiles/sass/`; ncu summaries: `profiles/ncu/
 | Subsystem | Here |
 |---|---|
 | 5.1 tracing / profiling | `dist/utils.py` (NVTX, cudaProfiler range), `tools/module_profiler.py`, `scripts/trace_step.py`, `scripts/profile_step.py`, `scripts/ncu_summary.py`, `docs/tools/profiling.md` |
-| 5.2 race detection / sanitizers | `scripts/run_sanitizer.sh` (memcheck / racecheck / synccheck, recorded in `profiles/r2/sanitizer.txt`), in-kernel spin watchdogs, protocol models `tests/test_attention_protocol.py`, device-lag experiment (`TDP_BENCH_GPU_LAG`), `docs/tools/sanitizer.md` |
+| 5.2 race detection / sanitizers | `scripts/run_sanitizer.sh` (memcheck / racecheck / synccheck, recorded in `profiles/r2/sanitizer.txt`), in-kernel spin watchdogs, protocol models `tests/test_attention_protocol.py` and `tests/test_collective_protocol.py`, device-lag experiment (`TDP_BENCH_GPU_LAG`), `docs/tools/sanitizer.md` |
 | 5.3 failure detection | {L('tools/watchdog.py', r'^class StepWatchdog')}, `tools/slurm_job_monitor.py` |
 | 5.4 checkpoint / resume | `dist/model_parallel_ckpt.py` (+ async writer), `state_dict` of `Bf16ZeroOptimizer` / `BucketAdamW` / `ShardedEMA`, resume-equivalence test |
 | 5.5 metrics / logging | {L('tools/metrics.py', r'^class MetricsLogger')}, `disable_non_master_print`, `report_memory` |
