@@ -242,3 +242,105 @@ def test_collective_protocol_model_detects_missing_ordering(kind, flaw):
         except AssertionError:
             failures += 1
     assert failures > 0, f"the model did not notice the missing edge {flaw!r}"
+
+
+# ------------------------------------------------------------------------------------------------
+# MoE dispatch / combine over peer memory (moe/layer.py _scatter / _gather): ping-pong halves and
+# ONE cross-GPU barrier per call.
+#   scatter, call c: clear half (c+1)&1 locally; store my routed rows into half c&1 of their owners;
+#                    barrier; read my half c&1.
+#   gather,  call c: write my slot rows into my half c&1; barrier; read the rows I need from the
+#                    peers' half c&1.
+# The claim to check: one barrier per call is enough because a half is only touched again two
+# calls later, with the barrier of the call in between separating the two uses.
+# ------------------------------------------------------------------------------------------------
+class A2AWorld(World):
+    def __init__(self, n, seed, halves=2):
+        super().__init__(n, 1, 1, seed)
+        self.halves = halves
+        # slots[rank][half][src] : "zero" | ("rows", call, src) | ("slot", call)
+        self.slots = [[{s: "zero" for s in range(n)} for _ in range(halves)] for _ in range(n)]
+        self.unread = [[set() for _ in range(halves)] for _ in range(n)]    # who still has to read
+
+
+def a2a_barrier(w, rank, slot, skip):
+    yield from block_barrier(w, rank, 0, ("a2a", slot), skip=skip)
+
+
+def scatter_rank(w, rank, calls, flaws):
+    H = w.halves
+    for c in range(calls):
+        use, other = c % H, (c + 1) % H
+        if H > 1:
+            for s in range(w.n):                               # clear the half of the NEXT call
+                assert s not in w.unread[rank][other], "cleared rows that were not read yet"
+                w.slots[rank][other][s] = "zero"
+                yield True
+        for p in w.rng.sample(range(w.n), w.n):                # my rows -> their owners
+            if H == 1 and w.slots[p][use][rank] != "zero":
+                # single buffer: the owner clears after reading; a store on top of unread rows
+                # or a clear on top of fresh rows is the race the ping-pong avoids
+                raise AssertionError("store into a slot that still holds the previous call's rows")
+            assert w.slots[p][use][rank] == "zero", \
+                f"rank {rank} call {c}: slot on rank {p} holds {w.slots[p][use][rank]}"
+            w.slots[p][use][rank] = ("rows", c, rank)
+            w.unread[p][use].add(rank)
+            yield True
+        yield from a2a_barrier(w, rank, c & 1, "no_barrier" in flaws)
+        for s in range(w.n):                                   # read what landed in my half
+            got = w.slots[rank][use][s]
+            assert got == ("rows", c, s), f"rank {rank} call {c}: read {got} from source {s}"
+            w.unread[rank][use].discard(s)
+            if H == 1:
+                w.slots[rank][use][s] = "zero"
+            yield True
+
+
+def gather_rank(w, rank, calls, flaws):
+    H = w.halves
+    for c in range(calls):
+        use = c % H
+        assert not w.unread[rank][use], \
+            f"rank {rank} call {c}: rewrote slot rows that ranks {sorted(w.unread[rank][use])} still need"
+        for s in range(w.n):
+            w.slots[rank][use][s] = ("slot", c)
+        w.unread[rank][use] = set(range(w.n))
+        yield True
+        yield from a2a_barrier(w, rank, c & 1, "no_barrier" in flaws)
+        for p in w.rng.sample(range(w.n), w.n):                # pull my rows from their owners
+            got = w.slots[p][use][rank]
+            assert got == ("slot", c), f"rank {rank} call {c}: read {got} from rank {p}"
+            w.unread[p][use].discard(rank)
+            yield True
+
+
+def simulate_a2a(role, n, seed, calls=6, halves=2, flaws=()):
+    w = A2AWorld(n, seed, halves)
+    for r in range(n):
+        w.spawn(role(w, r, calls, flaws))
+    w.run()
+    for r in range(n):
+        assert all(v == 0 for v in w.pad[r].values()), "a barrier signal was left behind"
+
+
+@pytest.mark.parametrize("role", [scatter_rank, gather_rank], ids=["dispatch", "combine"])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_moe_all_to_all_one_barrier_per_call(role, n):
+    for seed in range(10 if n < 8 else 4):
+        simulate_a2a(role, n, seed)
+
+
+@pytest.mark.parametrize("role,kw", [
+    (scatter_rank, dict(flaws=("no_barrier",))),     # reads rows that have not landed
+    (gather_rank, dict(flaws=("no_barrier",))),      # pulls rows the owner has not written
+    (scatter_rank, dict(halves=1)),                  # one buffer + one barrier: store races the clear
+    (gather_rank, dict(halves=1)),                   # one buffer + one barrier: rewrite under readers
+], ids=["dispatch-no-barrier", "combine-no-barrier", "dispatch-single-buffer", "combine-single-buffer"])
+def test_moe_all_to_all_model_detects_missing_ordering(role, kw):
+    failures = 0
+    for seed in range(40):
+        try:
+            simulate_a2a(role, 4, seed, **kw)
+        except AssertionError:
+            failures += 1
+    assert failures > 0
