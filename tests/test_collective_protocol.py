@@ -20,6 +20,9 @@ the collective kernels -- scheduled in random interleavings:
   before the kernel; the compute stream joins the communication stream before the optimizer /
   the next forward.
 
+Further down: the MoE dispatch / combine path (ping-pong halves, one barrier per call) and the
+fused sequence-parallel GEMMs (ping-pong halves, epoch flags, no barrier at all).
+
 Buffers carry version tags, so the model catches: a reduction that reads gradients which are not
 final, a peer's store landing in a buffer that is still being read, a consumer that sees
 un-reduced data, lost or duplicated barrier signals, and deadlocks.  The negative tests remove one
@@ -341,6 +344,80 @@ def test_moe_all_to_all_model_detects_missing_ordering(role, kw):
     for seed in range(40):
         try:
             simulate_a2a(role, 4, seed, **kw)
+        except AssertionError:
+            failures += 1
+    assert failures > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused sequence-parallel GEMMs (parallel/tensor_parallel/tp_fused.py _Region): all-gather -> GEMM
+# and GEMM -> reduce-scatter use ping-pong halves with epoch flags / counters and NO cross-GPU
+# barrier at all.  The claim: a rank can be at most one use ahead of its peers, because every use
+# ends in a wait on every peer's data of that use -- so when half k%2 is written again in use
+# k+2, all its readers of use k are done.
+# ------------------------------------------------------------------------------------------------
+class TpWorld(World):
+    def __init__(self, n, seed, halves):
+        super().__init__(n, 1, 1, seed)
+        self.halves = halves
+        self.buf = [[{s: None for s in range(n)} for _ in range(halves)] for _ in range(n)]
+        self.flag = [{s: 0 for s in range(n)} for _ in range(n)]      # AG: epoch per source chunk
+        self.counter = [0] * n                                        # RS: tiles landed at the owner
+
+
+def ag_gemm_rank(w, rank, uses):
+    for k in range(uses):
+        half = k % w.halves
+        for p in w.rng.sample(range(w.n), w.n):          # push my shard, then raise my chunk flag
+            w.buf[p][half][rank] = ("x", k, rank)
+            yield True
+            w.flag[p][rank] = k + 1                      # release store of the epoch
+            yield True
+        for i in range(w.n):                             # TMA producer: local chunk first
+            src = (rank + i) % w.n
+            yield from wait(lambda: w.flag[rank][src] >= k + 1)
+            for _ in range(2):                           # the chunk is read over many k-blocks
+                got = w.buf[rank][half][src]
+                assert got == ("x", k, src), f"rank {rank} use {k}: chunk of rank {src} holds {got}"
+                yield True
+
+
+def gemm_rs_rank(w, rank, uses):
+    for k in range(uses):
+        half = k % w.halves
+        for i in range(1, w.n + 1):                      # remote chunks first, own chunk last
+            owner = (rank + i) % w.n
+            w.buf[owner][half][rank] = ("part", k, rank)     # epilogue TMA store into the owner
+            yield True
+            w.counter[owner] += 1                            # release increment
+            yield True
+        yield from wait(lambda: w.counter[rank] >= (k + 1) * w.n)      # rs_reduce
+        for src in range(w.n):
+            got = w.buf[rank][half][src]
+            assert got == ("part", k, src), f"rank {rank} use {k}: partial of rank {src} is {got}"
+            yield True
+
+
+def simulate_tp(role, n, seed, uses=6, halves=2):
+    w = TpWorld(n, seed, halves)
+    for r in range(n):
+        w.spawn(role(w, r, uses))
+    w.run()
+
+
+@pytest.mark.parametrize("role", [ag_gemm_rank, gemm_rs_rank], ids=["ag_gemm", "gemm_rs"])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_fused_tp_ping_pong_needs_no_barrier(role, n):
+    for seed in range(10 if n < 8 else 4):
+        simulate_tp(role, n, seed)
+
+
+@pytest.mark.parametrize("role", [ag_gemm_rank, gemm_rs_rank], ids=["ag_gemm", "gemm_rs"])
+def test_fused_tp_single_buffer_would_race(role):
+    failures = 0
+    for seed in range(40):
+        try:
+            simulate_tp(role, 4, seed, halves=1)
         except AssertionError:
             failures += 1
     assert failures > 0
