@@ -206,6 +206,9 @@ SASS listings per kernel family: `profiles/sass/`; ncu summaries: `profiles/ncu/
 
 ## 2.5 Examples, explorations, docs
 
+Every script below runs to its "OK" line on CPU / gloo under torchrun in `tests/test_examples_cpu.py`
+(the reference's examples are its only tests; here they are exercised on every test run).
+
 {table(["ID", "Here"], rows_extra)}
 
 ## 2.6 Reference defects: intended behaviour, regression-tested
