@@ -207,6 +207,78 @@ def test_zero_optimizer_matches_adam(bucket_size, overlap):
     run_distributed(_w_zero, 2, bucket_size, overlap)
 
 
+def _w_zero_variants(rank, world, variant):
+    """Options of the reference constructor (zero_optim.py:108-109) and the shapes it is used in:
+    bf16 parameters with fp32 master weights, bf16 master weights, stage 1, no bucketing, gradient
+    accumulation, a non-Adam inner optimizer, two parameter groups, a world size that does not
+    divide anything nicely.  Reference: the same optimizer on one process with the world-averaged
+    loss (in fp32; the bf16 variants are compared after rounding the reference to bf16)."""
+    import torchdistpackage_b200 as tdp
+    tdp.fix_rand(0)
+    bf16 = variant in ("bf16_fp32_master", "bf16_master")
+    model = nn.Sequential(nn.Linear(16, 33), nn.GELU(), nn.Linear(33, 7))
+    ref = copy.deepcopy(model)
+    if bf16:
+        model = model.to(torch.bfloat16)
+    kw, acc = {}, 1
+    make = lambda ps: torch.optim.Adam(ps, lr=1e-2)
+    if variant == "bf16_master":
+        kw = dict(bf16_master_weights=True, bucketize=False)
+    elif variant == "stage1":
+        kw = dict(stage=1)
+    elif variant == "no_bucketize":
+        kw = dict(bucketize=False, overlap_comm=True)
+    elif variant == "grad_acc":
+        kw, acc = dict(grad_acc_steps=2, bucket_size=256, overlap_comm=True), 2
+    elif variant == "sgd_momentum":
+        make = lambda ps: torch.optim.SGD(ps, lr=2e-3, momentum=0.9, weight_decay=1e-2)
+    if variant == "two_groups":
+        groups = lambda m: [dict(params=[m[0].weight, m[0].bias], lr=1e-2),
+                            dict(params=[m[2].weight, m[2].bias], lr=3e-3, weight_decay=0.1)]
+        zopt = tdp.Bf16ZeroOptimizer(torch.optim.AdamW(groups(model)), bucket_size=300)
+        ref_opt = torch.optim.AdamW(groups(ref))
+    else:
+        zopt = tdp.Bf16ZeroOptimizer(make(model.parameters()), **kw)
+        ref_opt = make(ref.parameters())
+    assert len(zopt.param_groups) == len(ref_opt.param_groups)
+    for it in range(4):
+        ref_opt.zero_grad()
+        zopt.zero_grad()
+        for a in range(acc):
+            xs = []
+            for r in range(world):
+                torch.manual_seed(1000 * it + 10 * a + r)
+                xs.append(torch.randn(6, 16) + r)
+            x = xs[rank].to(torch.bfloat16) if bf16 else xs[rank]
+            (model(x).float().pow(2).sum() / acc).backward()
+            zopt.step()                      # counts micro-batches; acts on the last one
+            (sum(ref(x).pow(2).sum() for x in xs) / world / acc).backward()
+        ref_opt.step()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            if bf16:
+                # bf16 forward/backward noise: the trajectories agree to bf16 resolution
+                tol = 6e-2 if variant == "bf16_master" else 3e-2
+                assert (p.float() - q).abs().max() <= tol * q.abs().max() + 1e-2, (variant, it)
+            else:
+                assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (variant, it)
+    # every replica holds the same parameters bit for bit
+    flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()])
+    lo, hi = flat.clone(), flat.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi)
+    # optimizer state lives only for this rank's shard
+    n_total = sum(p.numel() for p in model.parameters())
+    n_state = sum(m.numel() for m in zopt.master)
+    assert n_state < n_total if world > 1 else n_state >= n_total
+
+
+@pytest.mark.parametrize("variant", ["bf16_fp32_master", "bf16_master", "stage1", "no_bucketize",
+                                     "grad_acc", "sgd_momentum", "two_groups"])
+def test_zero_optimizer_variants(variant):
+    run_distributed(_w_zero_variants, 3, variant)
+
+
 # ------------------------------------------------------------------ hybrid ZeRO (node-local shards)
 def _w_hybrid_zero(rank, world, mode, as_view, overlap):
     """4 ranks = 2 "nodes" x 2: ZeRO shards inside the node, the cross-node average comes from
