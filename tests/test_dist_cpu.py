@@ -107,6 +107,79 @@ def test_naive_ddp_matches_reference(as_view, sync, set_to_none):
     run_distributed(_w_ddp, 2, as_view, sync, set_to_none)
 
 
+class _Branchy(nn.Module):
+    """Mixed dtypes, a frozen parameter, a branch that some iterations do not use."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(10, 12)
+        self.b = nn.Linear(12, 12).double()             # second dtype -> its own buckets
+        self.skip = nn.Linear(12, 12)                   # used only when use_skip
+        self.frozen = nn.Linear(12, 12)
+        for q in self.frozen.parameters():
+            q.requires_grad_(False)
+        self.out = nn.Linear(12, 3)
+
+    def forward(self, x, use_skip):
+        h = torch.tanh(self.a(x))
+        h = self.b(h.double()).float() + self.frozen(h)
+        if use_skip:
+            h = h + self.skip(h)
+        return self.out(h)
+
+
+def _w_ddp_edge_cases(rank, world, as_view):
+    import torchdistpackage_b200 as tdp
+    tdp.fix_rand(0)
+    model = _Branchy()
+    ref = copy.deepcopy(model)
+    # per-parameter groups (every rank creates every group: new_group is collective); all ranks
+    # must route the same parameters to a sub-group so that the bucket layouts agree
+    sub01, sub2 = dist.new_group([0, 1]), dist.new_group([2]) if world == 3 else None
+
+    class PerParamGroup(tdp.NaiveDDP):                  # the reference's override hook (:95-96)
+        def _get_group(self, name, param):
+            if name.startswith("out."):
+                return sub01 if rank in (0, 1) else sub2
+            return self.group
+
+    cls = PerParamGroup if world == 3 else tdp.NaiveDDP
+    ddp = cls(model, gradient_as_bucket_view=as_view, bucket_cap_mb=2e-3)
+    assert not any(n.startswith("frozen") for n in ddp.reducer.param_bucket)
+    assert len({b.dtype for b in ddp.buckets}) == 2 and len(ddp.buckets) >= 3
+    for it in range(4):
+        use_skip = it % 2 == 0                          # odd iterations leave `skip` without grads
+        xs = []
+        for r in range(world):
+            torch.manual_seed(50 * it + r)
+            xs.append(torch.randn(4, 10))
+        ddp.zero_grad()
+        ddp(xs[rank], use_skip).sum().backward()
+        ddp.reduce_gradients()
+        ref.zero_grad()
+        (sum(ref(x, use_skip).sum() for x in xs) / world).backward()
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            if not p.requires_grad:
+                assert p.grad is None
+            elif n.startswith("out.") and world == 3:
+                # reduced over ranks {0, 1} only (rank 2 keeps its local gradient)
+                members = [0, 1] if rank in (0, 1) else [2]
+                ref2 = copy.deepcopy(ref)
+                ref2.zero_grad()
+                (sum(ref2(xs[m], use_skip).sum() for m in members) / len(members)).backward()
+                want = dict(ref2.named_parameters())[n].grad
+                assert torch.allclose(p.grad, want, atol=1e-5), (it, n)
+            elif n.startswith("skip.") and not use_skip:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, (it, n)
+            else:
+                assert torch.allclose(p.grad.to(q.grad.dtype), q.grad, atol=1e-5), (it, n)
+
+
+@pytest.mark.parametrize("world,as_view", [(2, True), (2, False), (3, True)])
+def test_naive_ddp_unused_frozen_mixed_dtype_and_per_param_groups(world, as_view):
+    run_distributed(_w_ddp_edge_cases, world, as_view)
+
+
 def _w_ddp_grad_acc(rank, world):
     import torchdistpackage_b200 as tdp
     tdp.fix_rand(0)
