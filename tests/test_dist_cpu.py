@@ -488,6 +488,89 @@ def test_pipeline_1f1b_matches_serial(pp, n_micro):
     run_distributed(_w_pipeline, pp, pp, n_micro)
 
 
+def _w_pipeline_scatter_gather_and_scaler(rank, world):
+    """pipe=2 x tensor=2: stage boundaries send only 1/tp of every activation / gradient and
+    all-gather it over the tensor group at the receiver (scatter_gather_tensors=True, reference
+    comm.py:108-155); forward_only=True runs the schedule without backward; NativeScalerPP drives
+    the loss scale around the schedule; partition_balanced splits by parameter count."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import forward_backward, NativeScalerPP, clip_grad_norm_
+    from torchdistpackage_b200.parallel.pipeline_parallel.pipeline_helper import partition_balanced
+    tdp.tpc.setup_process_groups([("pipe", 2), ("tensor", 2)])
+    tdp.fix_rand(0)
+    widths = [(12, 12), (12, 12), (12, 48), (48, 12)]           # unbalanced on purpose
+    layers = [nn.Linear(i, o) for i, o in widths]
+    full = nn.Sequential(*copy.deepcopy(layers))
+    mine = partition_balanced(layers)
+    pp_rank = tdp.tpc.get_pp_rank()
+    # balanced by parameters: 156+156+624 | 588  beats the uniform 2 | 2 split (312 | 1212)
+    assert len(mine) == (3 if pp_rank == 0 else 1), len(mine)
+    stage = nn.Sequential(*mine)
+    first, last = tdp.tpc.is_first_in_pipeline_group(), tdp.tpc.is_last_in_pipeline_group()
+    torch.manual_seed(3)
+    x, y = torch.randn(8, 12), torch.randn(8, 12)
+
+    def fwd(inp):
+        if last:
+            act, tgt = inp
+            return (stage(act) - tgt).pow(2).sum() / 8
+        return stage(inp)
+
+    inputs = [x] if first else [y]
+    opt = torch.optim.SGD(stage.parameters(), lr=0.1)
+    out = forward_backward(opt, fwd, None, inputs, num_microbatches=4, dtype=torch.float32,
+                           scatter_gather_tensors=True)
+    (full(x) - y).pow(2).sum().div(8).backward()
+    beg = 0 if pp_rank == 0 else 3
+    for i, lyr in enumerate(stage):
+        assert torch.allclose(lyr.weight.grad, full[beg + i].weight.grad, atol=1e-5), (pp_rank, i)
+    grads = [lyr.weight.grad.clone() for lyr in stage]
+
+    # forward_only: same loss on the last stage, no gradient touched
+    out2 = forward_backward(None, fwd, None, inputs, num_microbatches=4, forward_only=True,
+                            dtype=torch.float32, scatter_gather_tensors=True)
+    if last:
+        mb = slice(6, 8)                                          # the last micro-batch
+        want = (full(x[mb]) - y[mb]).pow(2).sum() / 8
+        assert torch.allclose(out2.detach(), want.detach(), atol=1e-5)
+    for g, lyr in zip(grads, stage):
+        assert torch.equal(g, lyr.weight.grad)
+
+    # AMP scaler front-end: backward already done by the schedule -> backward=False
+    scaler = NativeScalerPP(enabled=False)
+    before = [q.detach().clone() for q in stage.parameters()]
+    norm = scaler(out if last else None, opt, clip_grad=0.5, parameters=list(stage.parameters()),
+                  backward=False)
+    total = torch.sqrt(sum(q.grad.pow(2).sum() for q in full.parameters()))
+    assert torch.allclose(norm, total, rtol=1e-4), (float(norm), float(total))    # over both stages
+    coef = min(1.0, 0.5 / (float(total) + 1e-6))
+    for q0, q, g in zip(before, stage.parameters(), [t for lyr in stage for t in (lyr.weight.grad, lyr.bias.grad)]):
+        assert torch.allclose(q, q0 - 0.1 * g, atol=1e-6)          # grads were clipped in place
+    for g0, lyr in zip(grads, stage):
+        assert torch.allclose(lyr.weight.grad, g0 * coef, atol=1e-6)
+    assert isinstance(scaler.state_dict(), dict)
+
+    # enabled scaler, whole call (backward inside): an overflow on ONE stage must make every
+    # stage skip the step (found-inf is agreed on over the pipe and tensor groups)
+    scaler = NativeScalerPP(enabled=True, init_scale=4.0)
+    lin = nn.Linear(4, 4)
+    opt2 = torch.optim.SGD(lin.parameters(), lr=0.1)
+    w0 = lin.weight.detach().clone()
+    loss = lin(torch.ones(2, 4)).sum()
+    if rank == 3:
+        loss = loss * float("inf")
+    scaler(loss, opt2, clip_grad=1.0, parameters=list(lin.parameters()))
+    assert torch.equal(lin.weight.detach(), w0), "a stage stepped although another one overflowed"
+    assert scaler.state_dict()["scale"] < 4.0                      # backed off everywhere
+    opt2.zero_grad()
+    scaler(lin(torch.ones(2, 4)).sum(), opt2, clip_grad=1.0, parameters=list(lin.parameters()))
+    assert not torch.equal(lin.weight.detach(), w0)
+
+
+def test_pipeline_scatter_gather_forward_only_and_scaler():
+    run_distributed(_w_pipeline_scatter_gather_and_scaler, 4)
+
+
 def _w_pipeline_static_shapes(rank, world):
     """static_shapes=True: the shape handshake happens on the first call only; later calls must
     give the same results without any metadata message."""

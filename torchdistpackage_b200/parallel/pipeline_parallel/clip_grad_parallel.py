@@ -126,7 +126,8 @@ class NativeScalerPP:
         return self._scaler.scale(loss)
 
     def _sync_found_inf(self, optimizer) -> None:
-        st = self._scaler._per_optimizer_states.get(id(optimizer))
+        # (a disabled GradScaler never creates its per-optimizer state)
+        st = getattr(self._scaler, "_per_optimizer_states", {}).get(id(optimizer))
         if not st:
             return
         for t in st.get("found_inf_per_device", {}).values():
