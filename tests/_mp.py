@@ -19,6 +19,8 @@ def _entry(rank, world, port, backend, fn, args, err_q):
     for k in list(os.environ):
         if k.startswith("SLURM_"):
             os.environ.pop(k)
+    import _cov
+    _cov.start()
     try:
         import torchdistpackage_b200 as tdp
         tdp.tpc.reset()
@@ -28,6 +30,7 @@ def _entry(rank, world, port, backend, fn, args, err_q):
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+        _cov.dump()
     except Exception:
         err_q.put((rank, traceback.format_exc()))
         raise

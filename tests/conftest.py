@@ -22,3 +22,14 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "multigpu" in item.keywords and n_gpu < 2:
             item.add_marker(pytest.mark.skip(reason="needs >= 2 CUDA devices"))
+
+
+# optional function-level coverage (tests/_cov.py): TDP_COV_DIR=<dir> python -m pytest ...
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _cov  # noqa: E402
+
+_cov.start()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    _cov.dump()

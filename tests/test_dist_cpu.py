@@ -505,6 +505,9 @@ def _w_pipeline_scatter_gather_and_scaler(rank, world):
     pp_rank = tdp.tpc.get_pp_rank()
     # balanced by parameters: 156+156+624 | 588  beats the uniform 2 | 2 split (312 | 1212)
     assert len(mine) == (3 if pp_rank == 0 else 1), len(mine)
+    from torchdistpackage_b200.parallel.pipeline_parallel.pipeline_helper import flat_and_partition
+    nested = [nn.Linear(4, 4), [nn.ReLU(), nn.Linear(4, 4)], nn.Identity()]
+    assert len(flat_and_partition(nested, flat_level=1)) == 2            # 4 flat items over 2 stages
     stage = nn.Sequential(*mine)
     first, last = tdp.tpc.is_first_in_pipeline_group(), tdp.tpc.is_last_in_pipeline_group()
     torch.manual_seed(3)
@@ -959,3 +962,149 @@ def test_train_example_checkpoint_resume_reproduces_uninterrupted_run(tmp_path):
     rest = run(29683, "--steps", "6", "--resume", "--out", str(tmp_path / "part"))
     assert len(full) == 6 and part == full[:3] and rest == full[3:], (full, part, rest)
     assert (tmp_path / "part" / "metrics.jsonl").exists()
+
+
+# ------------------------------------------------------------------ remaining public surface
+def _w_topology_queries_and_checkpoint(rank, world, tmp):
+    """Every ``tpc`` query of the reference (process_topo.py:147-259) on an 8-rank
+    data x pipe x tensor layout; model-parallel checkpoint files written by DP replica 0 only,
+    sharded state per DP rank; EMA shard save / load; the bidirectional p2p wrappers."""
+    import os
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.dist.model_parallel_ckpt import save_mp_checkpoint, load_mp_checkpoint
+    from torchdistpackage_b200.dist.launch import get_cpu_group
+    from torchdistpackage_b200.parallel.pipeline_parallel import comm
+    from torchdistpackage_b200.parallel.tensor_parallel import tp_utils
+    tpc = tdp.tpc
+    tpc.setup_process_groups([("data", 2), ("pipe", 2), ("tensor", 2)])
+    dp, pp, tp = rank // 4, (rank // 2) % 2, rank % 2
+    assert (tpc.get_dp_rank(), tpc.get_pp_rank(), tpc.get_tp_rank()) == (dp, pp, tp)
+    assert (tpc.get_dp_size(), tpc.get_pp_size(), tpc.get_tp_size(), tpc.get_mp_size()) == (2, 2, 2, 4)
+    assert tpc.get_mp_rank() == rank % 4
+    assert tpc.is_first_in_tensor_group() == (tp == 0) and tpc.is_last_in_tensor_group() == (tp == 1)
+    assert tpc.is_first_in_data_group() == (dp == 0) and tpc.is_last_in_data_group() == (dp == 1)
+    assert tpc.is_first_in_model_group() == (rank % 4 == 0) and tpc.is_last_in_model_group() == (rank % 4 == 3)
+    assert tpc.is_first_in_pipeline_group() == (pp == 0) and tpc.is_last_in_pipeline_group() == (pp == 1)
+    assert tpc.all_dp_ranks() == [[0, 4], [1, 5], [2, 6], [3, 7]]
+    assert tpc.get_group("global") is None and tdp.is_using_pp()
+    assert tpc.get_prev_global_rank("pipe") == tpc.get_next_global_rank("pipe")     # ring of 2
+    assert tpc.setup_node_groups(4) is not None and tpc.get_group_size("node") == 4
+    assert get_cpu_group() is dist.group.WORLD                                      # gloo already
+    # TP helpers follow the module-level TP group
+    tp_utils.set_tp_group(tpc.get_group("tensor"))
+    assert tp_utils.get_tensor_model_parallel_world_size() == 2
+    x = torch.full((2, 3), float(tp))
+    shard = tp_utils.maybe_split_into_sequence_parallel(torch.arange(4.0).view(4, 1))
+    assert shard.shape[0] == 2 and tp_utils.is_squence_parallel_tensor(shard)
+    assert torch.equal(tp_utils.maybe_gather_from_sequence_parallel(shard), torch.arange(4.0).view(4, 1))
+    assert tp_utils.maybe_gather_from_sequence_parallel(x) is x                     # not SP: untouched
+    tp_utils.reset_tp_group()
+
+    # checkpoint naming + writers
+    prefix = os.path.join(tmp, "ckpt", "model")
+    assert tdp.get_mp_ckpt_suffix() == f"_tp_{tp}_pp_{pp}.pth"
+    path = save_mp_checkpoint(prefix, {"w": torch.full((2,), float(rank % 4))},
+                              sharded_state={"m": torch.full((1,), float(rank))})
+    assert path.endswith(f"_tp_{tp}_pp_{pp}.pth")
+    files = sorted(os.listdir(os.path.dirname(prefix)))
+    assert len([f for f in files if "_shard" not in f]) == 4 and len([f for f in files if "_shard" in f]) == 8
+    state, sh = load_mp_checkpoint(prefix, with_shard=True)
+    assert float(state["w"][0]) == rank % 4 and float(sh["m"][0]) == rank      # replica 0 wrote the model part
+
+    # EMA shard round trip
+    model = nn.Sequential(nn.Linear(4, 4), nn.Linear(4, 4))
+    ema = tdp.ShardedEMA(model, group=tpc.get_group("data"))
+    saved = {n: t.clone() for n, t in ema.state_dict_shard().items()}
+    ema.update(model, decay=0.5)
+    with torch.no_grad():
+        for q in model.parameters():
+            q.add_(1.0)
+    ema.update(model, decay=0.5)
+    assert any(not torch.equal(saved[n], t) for n, t in ema.state_dict_shard().items())
+    ema.load_state_dict_shard(saved)
+    assert all(torch.equal(saved[n], t) for n, t in ema.state_dict_shard().items())
+
+    # bidirectional wrappers between the two pipeline stages (each is the other's prev AND next)
+    a = torch.full((2, 3), float(rank))
+    peer = tpc.get_next_global_rank("pipe")
+    got = comm.send_forward_recv_forward(a, a.shape, dtype=torch.float32)
+    assert torch.equal(got, torch.full((2, 3), float(peer)))
+    got = comm.send_backward_recv_backward(a + 1, a.shape, dtype=torch.float32)
+    assert torch.equal(got, torch.full((2, 3), float(peer + 1)))
+
+
+def test_topology_queries_checkpoint_ema_shard_and_p2p_wrappers(tmp_path):
+    run_distributed(_w_topology_queries_and_checkpoint, 8, str(tmp_path))
+
+
+def _w_p2p_ring_exchange(rank, world):
+    """send_forward_backward_recv_forward_backward on a ring of 3 stages: one batched exchange
+    sends to both neighbours and receives from both (prev / next wrap around, as
+    tpc.get_prev/next_global_rank do in the reference, process_topo.py:222-234)."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel.pipeline_parallel import comm
+    tdp.tpc.setup_process_groups([("pipe", 3)])
+    prev, nxt = tdp.tpc.get_prev_global_rank("pipe"), tdp.tpc.get_next_global_rank("pipe")
+    assert (prev, nxt) == ((rank - 1) % 3, (rank + 1) % 3)
+    a = torch.full((2, 3), float(rank))
+    for _ in range(2):
+        t, g = comm.send_forward_backward_recv_forward_backward([a, a * 10], a + 100, [a.shape, a.shape],
+                                                                 a.shape, dtype=torch.float32)
+        assert torch.equal(t[0], torch.full((2, 3), float(prev))) and torch.equal(t[1], torch.full((2, 3), 10.0 * prev))
+        assert torch.equal(g, torch.full((2, 3), float(nxt + 100)))
+
+
+def test_pipeline_p2p_bidirectional_ring_exchange():
+    run_distributed(_w_p2p_ring_exchange, 3)
+
+
+def _w_ddp_small_api(rank, world):
+    """NaiveDDP / MoEDP methods around the main loop: hook removal, re-broadcast, accumulation
+    count, manual dispatch, comm sync; Bf16ZeroOptimizer.state passthrough."""
+    import torchdistpackage_b200 as tdp
+    tdp.fix_rand(rank)                               # replicas start different
+    model = TinyMLP()
+    ddp = tdp.NaiveDDP(model, gradient_as_bucket_view=True)
+    ddp.sync_comm()
+    ddp.set_num_grad_acc_iter(2)
+    for mb in range(2):
+        torch.manual_seed(10 * mb + rank)
+        ddp(torch.randn(3, 10)).sum().backward()
+    ddp.reduce_gradients()
+    g = model.fc1.weight.grad.clone()
+    gs = [torch.empty_like(g) for _ in range(world)]
+    dist.all_gather(gs, g)
+    assert all(torch.allclose(gs[0], t) for t in gs)             # reduced once, after 2 micro-batches
+    with torch.no_grad():
+        model.fc1.weight.add_(float(rank))                       # drift apart ...
+    ddp.broadcast_params()                                       # ... and re-sync from rank 0
+    ws = [torch.empty_like(model.fc1.weight) for _ in range(world)]
+    dist.all_gather(ws, model.fc1.weight.detach())
+    assert all(torch.equal(ws[0], t) for t in ws)
+    ddp.remove_hooks()
+    ddp.zero_grad()
+    torch.manual_seed(100 + rank)
+    model(torch.randn(3, 10)).sum().backward()
+    ddp.reduce_gradients()                                       # finalize still reduces what it holds
+    assert not hasattr(model.fc1.weight, "_tdp_reducer")
+
+    # MoEDP on a sub-group: manual dispatch of a gradient produced outside autograd
+    experts = {"e.w": nn.Parameter(torch.full((4, 4), float(rank)))}
+    mo = tdp.create_moe_dp_hooks(experts, None, 0, overlap_comm=True)
+    assert torch.equal(experts["e.w"].detach(), torch.zeros(4, 4))      # broadcast from rank 0
+    experts["e.w"].grad = None
+    (experts["e.w"] * float(rank + 1)).sum().backward()
+    tdp.moe_dp_iter_step()
+    assert torch.allclose(experts["e.w"].grad, torch.full((4, 4), sum(range(1, world + 1)) / world))
+    with torch.no_grad():
+        experts["e.w"].add_(float(rank))
+    mo.broadcast_params()
+    assert torch.equal(experts["e.w"].detach(), torch.zeros(4, 4))
+    mo.remove_hooks()
+
+    z = tdp.Bf16ZeroOptimizer(torch.optim.Adam(TinyMLP().parameters(), lr=1e-3))
+    assert isinstance(z.state, dict) or hasattr(z.state, "keys")
+
+
+def test_naive_ddp_and_moe_dp_small_api():
+    run_distributed(_w_ddp_small_api, 2)
