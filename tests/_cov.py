@@ -30,7 +30,15 @@ def start() -> None:
         return mon.DISABLE
 
     mon.register_callback(mon.COVERAGE_ID, mon.events.PY_START, on_start)
-    mon.set_events(mon.COVERAGE_ID, mon.events.PY_START)
+    events = mon.events.PY_START
+    if os.environ.get("TDP_COV_LINES"):                 # line mode: also which lines ran
+        def on_line(code, line):
+            if code.co_filename.startswith(PKG):
+                _seen.add((os.path.relpath(code.co_filename, PKG), int(line)))
+            return mon.DISABLE
+        mon.register_callback(mon.COVERAGE_ID, mon.events.LINE, on_line)
+        events |= mon.events.LINE
+    mon.set_events(mon.COVERAGE_ID, events)
 
 
 def dump() -> None:
@@ -39,7 +47,7 @@ def dump() -> None:
         return
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"{os.getpid()}.json"), "w") as f:
-        json.dump(sorted(_seen), f)
+        json.dump(sorted(_seen, key=lambda t: (t[0], str(t[1]))), f)
 
 
 def _functions():
@@ -64,12 +72,53 @@ def _functions():
             yield from walk(tree, "")
 
 
+def _executable_lines(path):
+    """Line numbers that carry code, from the compiled code objects (docstrings excluded)."""
+    lines = set()
+    todo = [compile(open(path).read(), path, "exec")]
+    while todo:
+        co = todo.pop()
+        doc = co.co_consts[0] if co.co_consts and isinstance(co.co_consts[0], str) else None
+        for _, _, ln in co.co_lines():
+            if ln is not None:
+                lines.add(ln)
+        todo += [c for c in co.co_consts if hasattr(c, "co_lines")]
+    return lines
+
+
+def _line_report(seen, only):
+    ran = {}
+    for item in seen:
+        if isinstance(item[1], int):
+            ran.setdefault(item[0], set()).add(item[1])
+    for rel in sorted(ran):
+        if only and not any(o in rel for o in only):
+            continue
+        src = open(os.path.join(PKG, rel)).read().splitlines()
+        todo = sorted(_executable_lines(os.path.join(PKG, rel)) - ran[rel])
+        todo = [ln for ln in todo if not src[ln - 1].lstrip().startswith(('"""', "def ", "class ", "@"))]
+        print(f"== {rel}: {len(todo)} executable lines never ran")
+        start = prev = None
+        for ln in todo + [None]:
+            if start is None:
+                start = prev = ln
+            elif ln is not None and ln <= prev + 2:
+                prev = ln
+            else:
+                print(f"   {start}-{prev}: {src[start - 1].strip()[:90]}")
+                start = prev = ln
+
+
 if __name__ == "__main__":
     d = sys.argv[1]
     seen = set()
     for f in os.listdir(d):
         if f.endswith(".json"):
             seen |= {tuple(x) for x in json.load(open(os.path.join(d, f)))}
+    if len(sys.argv) > 2 and sys.argv[2] == "--lines":
+        _line_report(seen, sys.argv[3:])
+        sys.exit(0)
+    seen = {x for x in seen if isinstance(x[1], str)}
     funcs = sorted(set(_functions()))
     missed = [(r, q, ln) for r, q, ln in funcs if (r, q) not in seen]
     print(f"{len(funcs) - len(missed)} / {len(funcs)} functions ran")

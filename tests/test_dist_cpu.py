@@ -1151,3 +1151,92 @@ def test_setup_distributed_from_slurm_environment():
     while not q.empty():
         msgs.append(q.get())
     assert all(p.exitcode == 0 for p in procs) and not msgs, msgs
+
+
+# ------------------------------------------------------------------ user-side habits the engines must survive
+def _w_engine_edge_paths(rank, world):
+    """``zero_grad(set_to_none=True)`` (the torch default) under the ZeRO optimizer: the
+    gradient views are dropped, autograd creates fresh tensors, the hook re-attaches them.
+    Resume from a checkpoint continues the exact trajectory; a checkpoint of another layout is
+    refused.  NaiveDDP in copy mode with a parameter that got no gradient."""
+    import torchdistpackage_b200 as tdp
+
+    def data(it):
+        xs = []
+        for r in range(world):
+            torch.manual_seed(31 * it + r)
+            xs.append(torch.randn(5, 10))
+        return xs
+
+    tdp.fix_rand(0)
+    model = TinyMLP()
+    ref = copy.deepcopy(model)
+    zopt = tdp.Bf16ZeroOptimizer(torch.optim.Adam(model.parameters(), lr=1e-2), bucket_size=128,
+                                 overlap_comm=True)
+    ref_opt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    sd = None
+    for it in range(6):
+        xs = data(it)
+        for p in model.parameters():
+            p.grad = None                                  # what optimizer.zero_grad() does by default
+        for mg in zopt.master_grad:
+            mg.zero_()
+        model(xs[rank]).sum().backward()
+        zopt.step()
+        ref_opt.zero_grad()
+        (sum(ref(x).sum() for x in xs) / world).backward()
+        ref_opt.step()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, atol=1e-6), it
+        if it == 2:
+            sd = copy.deepcopy(zopt.state_dict())
+            snap = [p.detach().clone() for p in model.parameters()]
+    final = [p.detach().clone() for p in model.parameters()]
+
+    # resume from step 3 in a fresh optimizer object: same end point
+    tdp.fix_rand(1)
+    model2 = TinyMLP()
+    with torch.no_grad():
+        for p, s_ in zip(model2.parameters(), snap):
+            p.copy_(s_)
+    zopt2 = tdp.Bf16ZeroOptimizer(torch.optim.Adam(model2.parameters(), lr=1e-2), bucket_size=128,
+                                  overlap_comm=True)
+    zopt2.load_state_dict(sd)
+    for it in range(3, 6):
+        zopt2.zero_grad(set_to_none=True)
+        model2(data(it)[rank]).sum().backward()
+        zopt2.step()
+    for p, q in zip(model2.parameters(), final):
+        assert torch.allclose(p, q, atol=1e-6)
+    bad = copy.deepcopy(sd)
+    bad["layout"]["world"] = world + 1
+    with pytest.raises(ValueError):
+        zopt2.load_state_dict(bad)
+    with pytest.raises(TypeError):                         # one dtype per optimizer (as the reference)
+        mixed = [nn.Parameter(torch.zeros(4)), nn.Parameter(torch.zeros(4, dtype=torch.float64))]
+        tdp.Bf16ZeroOptimizer(torch.optim.Adam(mixed, lr=1e-3))
+
+    # NaiveDDP, copy mode (no bucket views), one parameter without gradient on odd steps
+    model3 = _Branchy()
+    ref3 = copy.deepcopy(model3)
+    ddp = tdp.NaiveDDP(model3, gradient_as_bucket_view=False, bucket_cap_mb=1e-3)
+    for it in range(3):
+        xs = [x[:, :10] for x in data(it)]
+        ddp.zero_grad(set_to_none=True)
+        ddp(xs[rank], it % 2 == 0).sum().backward()
+        ddp.reduce_gradients()
+        ref3.zero_grad()
+        (sum(ref3(x, it % 2 == 0).sum() for x in xs) / world).backward()
+        for (n, p), (_, q) in zip(model3.named_parameters(), ref3.named_parameters()):
+            if q.grad is None or (n.startswith("skip.") and it % 2 == 1):
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, (it, n)
+            else:
+                assert torch.allclose(p.grad.to(q.grad.dtype), q.grad, atol=1e-5), (it, n)
+    with pytest.raises(ValueError):
+        tdp.NaiveDDP(TinyMLP(), reduce_op="max")
+    with pytest.raises(TypeError):
+        tdp.NaiveDDP(TinyMLP(), no_such_option=1)
+
+
+def test_engines_survive_set_to_none_resume_and_unused_parameters():
+    run_distributed(_w_engine_edge_paths, 2)
