@@ -1240,3 +1240,103 @@ def _w_engine_edge_paths(rank, world):
 
 def test_engines_survive_set_to_none_resume_and_unused_parameters():
     run_distributed(_w_engine_edge_paths, 2)
+
+
+def _w_pipeline_multi_tensor_boundary(rank, world):
+    """Stages hand over TWO tensors (hidden state + a skip stream), the user supplies bwd_fn
+    (reference pipeline_sched.py:36-69; its `cur_inputs.append(*input_obj_from_prev)` only works
+    for one tensor, :24), 3 stages, 3 micro-batches."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import forward_backward, forward_eval
+    tdp.tpc.setup_process_groups([("pipe", 3)])
+    tdp.fix_rand(0)
+    layers = [nn.Linear(6, 6) for _ in range(3)]
+    full = copy.deepcopy(layers)
+    mine = layers[rank]
+    first, last = rank == 0, rank == 2
+    torch.manual_seed(11)
+    x, y = torch.randn(6, 6), torch.randn(6, 6)
+    calls = []
+
+    def fwd(inp):
+        if first:
+            h = mine(inp)
+            return [h, inp * 2.0]                            # (hidden, skip)
+        if last:
+            h, skip, tgt = inp
+            return ((mine(h) + skip - tgt) ** 2).sum() / 6
+        h, skip = inp
+        return [torch.tanh(mine(h)), skip + h]
+
+    def bwd(output, output_grad):
+        calls.append(1)
+        if output_grad is None:
+            output.backward()
+        else:
+            pairs = [(o, g) for o, g in zip(output, output_grad) if o.requires_grad]
+            torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
+
+    inputs = [x] if first else ([y] if last else None)
+    opt = torch.optim.SGD(mine.parameters(), lr=0.1)
+    out = forward_backward(opt, fwd, bwd, inputs, num_microbatches=3, dtype=torch.float32)
+    assert len(calls) == 3
+    g_user = [mine.weight.grad.clone(), mine.bias.grad.clone()]
+    # the built-in backward gives the same gradients (stage 0 forwards plain data as its 2nd output)
+    forward_backward(opt, fwd, None, inputs, num_microbatches=3, dtype=torch.float32)
+    assert torch.allclose(mine.weight.grad, g_user[0], atol=1e-6)
+    assert torch.allclose(mine.bias.grad, g_user[1], atol=1e-6)
+    # oracle
+    xr = x.clone().requires_grad_(True)
+    h0 = full[0](xr)
+    h1 = torch.tanh(full[1](h0))
+    loss = ((full[2](h1) + (xr * 2.0 + h0) - y) ** 2).sum() / 6
+    loss.backward()
+    assert torch.allclose(mine.weight.grad, full[rank].weight.grad, atol=1e-5), rank
+    assert torch.allclose(mine.bias.grad, full[rank].bias.grad, atol=1e-5), rank
+    with torch.no_grad():
+        o = forward_eval(fwd, [x] if first else ([y] if last else None), dtype=torch.float32)
+        if last:
+            assert torch.allclose(o, loss.detach(), atol=1e-5)
+
+
+def test_pipeline_multi_tensor_stage_boundary_with_user_backward():
+    run_distributed(_w_pipeline_multi_tensor_boundary, 3)
+
+
+def _w_clip_variants(rank, world):
+    """clip_grad_norm_ corners: a single tensor, the max norm across model-parallel groups,
+    the non-finite check, nothing to clip; q/k/v-aligned weight slicing with a bias."""
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import clip_grad_norm_, ColParallelLinear
+    tdp.tpc.setup_process_groups([("pipe", 2), ("tensor", 2)])
+    p = nn.Parameter(torch.zeros(4))
+    p.grad = torch.full((4,), float(rank + 1))
+    p.is_tp_shard = True
+    n = clip_grad_norm_(p, max_norm=100.0, norm_type=float("inf"))
+    assert float(n) == 4.0                                    # max over all 4 ranks
+    n2 = clip_grad_norm_(p, max_norm=1.0)                     # shards: sum of squares over tp and pp
+    assert torch.allclose(n2, torch.tensor(4 * (1 + 4 + 9 + 16.0)).sqrt())
+    assert torch.allclose(p.grad.norm(), torch.tensor(2.0 * (rank + 1)) / n2, rtol=1e-4)
+    q = nn.Parameter(torch.zeros(2))
+    assert float(clip_grad_norm_([q], 1.0)) == 0.0            # no gradients at all
+    p.grad = torch.full((4,), float("nan") if rank == 3 else 1.0)
+    with pytest.raises(RuntimeError):
+        clip_grad_norm_([p], 1.0, error_if_nonfinite=True)    # every rank sees the agreed norm
+
+    from torchdistpackage_b200.parallel.tensor_parallel import tp_utils
+    tp_utils.set_tp_group(tdp.tpc.get_group("tensor"))
+    tp = tdp.tpc.get_tp_rank()
+    col = ColParallelLinear(4, 12, bias=True)
+    full_w = torch.arange(48.0).view(4, 12)                   # [fin, 3*dim]: q | k | v thirds
+    full_b = torch.arange(12.0)
+    with torch.no_grad():
+        col.init_weight_from_full_attn(full_w, full_b)
+    want = torch.cat([t.split(2, dim=-1)[tp] for t in full_w.split(4, dim=-1)], dim=-1)
+    assert torch.equal(col.linear.weight.detach(), want)      # heads stay aligned per projection
+    want_b = torch.cat([t.split(2)[tp] for t in full_b.split(4)])
+    assert torch.equal(col.linear.bias.detach(), want_b)
+    tp_utils.reset_tp_group()
+
+
+def test_clip_grad_norm_variants_and_attention_weight_slicing():
+    run_distributed(_w_clip_variants, 4)

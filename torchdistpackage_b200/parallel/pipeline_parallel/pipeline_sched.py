@@ -58,7 +58,12 @@ def _backward_step(input_obj, output_obj, output_grad, bwd_fn: Optional[Callable
     else:
         outs = [output_obj] if isinstance(output_obj, torch.Tensor) else list(output_obj)
         grads = [output_grad] if isinstance(output_grad, torch.Tensor) else list(output_grad)
-        torch.autograd.backward(tensors=outs, grad_tensors=grads)
+        # a stage may pass plain data along (e.g. a mask or an untouched input): nothing to
+        # differentiate there, the gradient the next stage sent for it is dropped
+        pairs = [(o, g) for o, g in zip(outs, grads) if o.requires_grad]
+        if pairs:
+            torch.autograd.backward(tensors=[o for o, _ in pairs],
+                                    grad_tensors=[g for _, g in pairs])
     if input_obj is None:
         return None
     if isinstance(input_obj, torch.Tensor):
