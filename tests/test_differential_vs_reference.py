@@ -1,0 +1,199 @@
+"""Differential tests: the pure (device-free) pieces of the reference, imported from the
+unmodified install under ``baseline/_ref`` (the benchmark's reference arm), are run side by side
+with this package on the same inputs.  Skipped when the reference is not installed.
+
+Covered: rank layouts of every axis and of the automatic model group for many world sizes / axis
+orders, MoE group splits, uniform pipeline partition, model flattening helpers, greedy parameter
+partition (EMA / ZeRO utility), bucket slot alignment, the bus-bandwidth convention, profiler
+level rule and the NaN helpers' polarity.  Where the reference is known to be wrong (SURVEY.md
+2.6) the test pins the *intended* behaviour instead and says so."""
+import itertools
+import os
+import sys
+from collections import defaultdict
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_DIR, "torchdistpackage")),
+                                reason="reference arm not installed (baseline/_ref)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, REF_DIR)
+    try:
+        import torchdistpackage as r
+        import torchdistpackage.dist.process_topo as r_topo
+        import torchdistpackage.parallel.pipeline_parallel.pipeline_helper as r_ph
+        import torchdistpackage.utils as r_utils
+        import torchdistpackage.ddp.zero_optim as r_zero
+        import torchdistpackage.ddp.naive_ddp as r_ddp
+        import torchdistpackage.dist.py_comm_test as r_comm
+        import torchdistpackage.tools.module_profiler as r_prof
+        import torchdistpackage.tools.debug_nan as r_nan
+    finally:
+        sys.path.remove(REF_DIR)
+    return dict(root=r, topo=r_topo, ph=r_ph, utils=r_utils, zero=r_zero, ddp=r_ddp, comm=r_comm,
+                prof=r_prof, nan=r_nan)
+
+
+def _reference_layout(r_topo, monkeypatch, world, config, moe=None):
+    """Run the reference's own ProcessTopology with torch.distributed stubbed out and collect the
+    rank lists it would create, in creation order."""
+    created = defaultdict(list)
+    monkeypatch.setattr(r_topo.dist, "get_world_size", lambda group=None: world)
+    monkeypatch.setattr(r_topo.dist, "get_rank", lambda group=None: 0)
+    monkeypatch.setattr(r_topo.dist, "new_group", lambda ranks, **kw: tuple(ranks))
+    topo = object.__new__(r_topo.ProcessTopology)          # bypass the singleton
+    topo.__init__()
+    real_build = topo._build_group
+
+    def build(type, ranks):
+        created[type].append(list(ranks))
+        real_build(type, ranks)
+    topo._build_group = build
+    import builtins
+    monkeypatch.setattr(builtins, "print", lambda *a, **k: None)
+    topo.setup_process_groups(config)
+    if moe is not None:
+        topo.build_moe_groups(**moe)
+    return dict(created)
+
+
+CONFIGS = []
+for world in (8, 16, 32, 64):
+    for sizes in ((2, 2), (2, 4), (4, 2)):
+        rest = world // (sizes[0] * sizes[1])
+        if rest < 1:
+            continue
+        for order in itertools.permutations([("data", rest), ("pipe", sizes[0]), ("tensor", sizes[1])]):
+            CONFIGS.append((world, list(order)))
+CONFIGS += [(8, [("data", 8)]), (8, [("data", 4), ("tensor", 2)]), (12, [("pipe", 3), ("data", 4)]),
+            (16, [("data", 4.0), ("pipe", 2), ("tensor", 2)])]        # float sizes, as in the Readme
+
+
+@pytest.mark.parametrize("world,config", CONFIGS, ids=lambda v: str(v) if isinstance(v, int) else
+                         "x".join(f"{n[0]}{int(s)}" for n, s in v))
+def test_rank_layouts_match_the_reference(ref, monkeypatch, world, config):
+    from torchdistpackage_b200.dist.process_topo import compute_layout
+    want = _reference_layout(ref["topo"], monkeypatch, world, config)
+    got = compute_layout(world, config)
+    assert set(got) == set(want)
+    for axis in want:
+        assert got[axis] == want[axis], axis               # same groups in the same creation order
+
+
+@pytest.mark.parametrize("world,dp,kw", [(8, 8, dict(moe_ep_size=4)), (8, 8, dict(moe_dp_size=4)),
+                                         (16, 8, dict(moe_ep_size=2, moe_dp_size=4)),
+                                         (16, 4, dict(moe_ep_size=4)), (32, 8, dict(moe_dp_size=2))])
+def test_moe_group_split_matches_the_reference(ref, monkeypatch, world, dp, kw):
+    from torchdistpackage_b200.dist.process_topo import compute_layout, compute_moe_layout
+    config = [("data", dp), ("tensor", world // dp)] if world != dp else [("data", dp)]
+    r_topo = ref["topo"]
+    monkeypatch.setattr(r_topo.ProcessTopology, "get_dp_size", lambda self: dp, raising=False)
+    want = _reference_layout(r_topo, monkeypatch, world, config, moe=kw)
+    ep_groups, dp_groups, ep, mdp = compute_moe_layout(compute_layout(world, config)["data"], **kw)
+    assert ep * mdp == dp
+    assert ep_groups == want["moe_ep"] and dp_groups == want["moe_dp"]
+
+
+def test_uniform_partition_and_flatten_helpers_match(ref, monkeypatch):
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel.pipeline_parallel import pipeline_helper as ph
+    r_ph = ref["ph"]
+    for n_items in range(1, 14):
+        for pp in range(1, 6):
+            for extra in (0, 1, 3):
+                for rank in range(pp):
+                    for mod, topo in ((r_ph, r_ph.tpc), (ph, ph.tpc)):
+                        monkeypatch.setattr(type(topo), "get_group_rank", lambda self, m, r=rank: r)
+                        monkeypatch.setattr(type(topo), "get_group_size", lambda self, m, w=pp: w)
+                    items = list(range(n_items))
+                    assert ph.partition_uniform(items, extra) == r_ph.partition_uniform(items, extra), \
+                        (n_items, pp, extra, rank)
+    monkeypatch.undo()
+    seq = [nn.Sequential(nn.Linear(2, 2)), nn.Sequential(nn.ReLU(), nn.Sequential(nn.Tanh(), nn.Sigmoid())),
+           [nn.GELU()]]
+    for level in (0, 1):
+        a, b = ph.flatten_sequence(seq, level), r_ph.flatten_sequence(seq, level)
+        assert [type(x) for x in a] == [type(x) for x in b], level
+    # unevenly nested input: the reference iterates into a leaf module and raises (:126); here a
+    # leaf reached early simply stays a leaf
+    uneven = [nn.Linear(2, 2), nn.Sequential(nn.ReLU(), nn.Sequential(nn.Tanh(), nn.Sigmoid()))]
+    with pytest.raises(TypeError):
+        r_ph.flatten_sequence(uneven, 2)
+    assert [type(x).__name__ for x in ph.flatten_sequence(uneven, 2)] == ["Linear", "ReLU", "Tanh", "Sigmoid"]
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Linear(4, 4)
+            self.body = nn.Sequential(nn.ReLU(), nn.Linear(4, 4))
+            self.blocks = nn.ModuleList([nn.Tanh(), nn.Linear(4, 2)])
+    net = Net()
+    order = ["stem", "body", lambda x: x * 2.0, "blocks", nn.Softmax(dim=-1)]
+    ours, theirs = ph.flatten_model(net, order, return_list=True), r_ph.flatten_model(net, order, return_list=True)
+    assert [type(m).__name__ for m in ours] == [type(m).__name__ for m in theirs]
+    x = torch.randn(3, 4)
+    assert torch.allclose(ph.flatten_model(net, order)(x), r_ph.flatten_model(net, order)(x))
+    assert isinstance(ph.CallableModule(lambda t: t + 1)(x), torch.Tensor)
+    del tdp
+
+
+def test_parameter_partition_bucket_alignment_and_conventions_match(ref):
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.ddp.zero_optim import partition_params as zero_partition
+    from torchdistpackage_b200.ddp.naive_ddp import GradBucket
+    from torchdistpackage_b200.dist.py_comm_test import mode_2_frac, bus_bandwidth_gbs
+    from torchdistpackage_b200.tools.module_profiler import get_level, count_tensor_size
+    from torchdistpackage_b200.tools import debug_nan
+    torch.manual_seed(0)
+    for widths in ([8, 8, 8, 8], [3, 50, 7, 7, 20], [64, 2, 2, 2, 2, 2], [5]):
+        layers = [nn.Linear(a, b) for a, b in zip([4] + widths[:-1], widths)]
+        model = nn.Sequential(*layers)
+        for n in (1, 2, 3, 4):
+            ours = tdp.partition_params(model, n, return_dict=True)
+            theirs = ref["utils"].partition_params(model, n, return_dict=True)
+            if len(theirs) == n and sum(len(t) for t in theirs) == len(list(model.parameters())):
+                # (the reference overruns its partition list for some shapes: IndexError / lost
+                # parameters -- compare only where it produced a complete answer)
+                covered = [k for part in ours for k in part]
+                assert covered == [k for k, _ in model.named_parameters()]
+                assert [list(p) for p in ours] == [list(p) for p in theirs], (widths, n)
+            assert len(tdp.partition_params(model, n)) == n
+    ps = [torch.zeros(k) for k in (10, 20, 5, 40, 8, 8)]
+    assert [[t.numel() for t in part] for part in zero_partition(ps, 3, 30)] == \
+           [[t.numel() for t in part] for part in ref["zero"].partition_params(ps, 3, 30)]
+
+    ours_b = GradBucket(0, torch.float32, torch.device("cpu"), None, 4096)
+    theirs_b = ref["ddp"].GradBucket("b", 4096 * 4, 4, (torch.float32, torch.device("cpu"), None))
+    for numel in (1, 100, 127, 128, 129, 1000):
+        for dt in (torch.float32, torch.bfloat16):
+            t = torch.zeros(numel, dtype=dt)
+            want = theirs_b.get_aligned_size(t)            # 512-byte slots, in elements of t
+            ob = GradBucket(0, dt, torch.device("cpu"), None, 4096)
+            assert ob.get_aligned_size(t) == want, (numel, dt)
+    del ours_b
+
+    assert {k: float(v) for k, v in ref["comm"].mode_2_frac.items()} == \
+           {k: float(mode_2_frac[k]) for k in ref["comm"].mode_2_frac}
+    assert abs(bus_bandwidth_gbs("all_reduce", 8 * 10 ** 9, 2.0, 8) - 4.0 * 2 * 7 / 8) < 1e-9
+
+    for name in ("root", "conv1", "layer1", "layer1.0", "layer1.0.conv1", "blocks.3.attn.qkv", "a.b.c"):
+        assert get_level(name) == ref["prof"].get_level(name), name
+    assert get_level("blocks.12.attn") == 2                # the reference says 3: two-digit index
+    assert ref["prof"].get_level("blocks.12.attn") == 3
+    t = [torch.zeros(3), (torch.zeros(2, 2, dtype=torch.bfloat16),)]
+    assert count_tensor_size(t) == ref["prof"].count_tensor_size(t) == 12 + 8
+    assert count_tensor_size(torch.zeros(5, dtype=torch.int8)) == 5     # reference: 40 (defect #14)
+
+    clean, dirty = torch.ones(3), torch.tensor([1.0, float("inf")])
+    for fn in ("check_tensor_inf_nan", "check_tensors"):
+        assert getattr(debug_nan, fn)(clean) == getattr(ref["nan"], fn)(clean) is True
+        assert getattr(debug_nan, fn)(dirty) == getattr(ref["nan"], fn)(dirty) is False
+    assert debug_nan.check_tensors([clean, dirty]) == ref["nan"].check_tensors([clean, dirty]) is False
