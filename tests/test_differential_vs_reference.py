@@ -197,3 +197,44 @@ def test_parameter_partition_bucket_alignment_and_conventions_match(ref):
         assert getattr(debug_nan, fn)(clean) == getattr(ref["nan"], fn)(clean) is True
         assert getattr(debug_nan, fn)(dirty) == getattr(ref["nan"], fn)(dirty) is False
     assert debug_nan.check_tensors([clean, dirty]) == ref["nan"].check_tensors([clean, dirty]) is False
+
+
+def test_transformer_blocks_are_state_dict_compatible_and_numerically_equal(ref):
+    """The serial model family (reference parallel/tensor_parallel/{attn,mlp,transformer}.py):
+    same parameter names and shapes -- a reference checkpoint loads here unchanged -- and the same
+    function: forward output, input gradient and every parameter gradient agree."""
+    sys.path.insert(0, REF_DIR)
+    try:
+        from torchdistpackage.parallel.tensor_parallel.transformer import Block as RBlock
+        from torchdistpackage.parallel.tensor_parallel.attn import Attention as RAttention
+        from torchdistpackage.parallel.tensor_parallel.mlp import Mlp as RMlp
+    finally:
+        sys.path.remove(REF_DIR)
+    from torchdistpackage_b200.parallel import Block, Attention, Mlp
+    torch.manual_seed(0)
+    cases = [(RBlock(32, 4, 4), Block(32, 4, 4)),
+             (RAttention(32, num_heads=4, qkv_bias=True), Attention(32, num_heads=4, qkv_bias=True)),
+             (RMlp(32, 64, 32), Mlp(32, 64, 32))]
+    for theirs, ours in cases:
+        sd = theirs.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == \
+               [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+        with torch.no_grad():                        # the reference initialises biases to zero:
+            for k, v in sd.items():                  # give them values so that they matter
+                if k.endswith("bias"):
+                    v.normal_(std=0.1)
+        theirs.load_state_dict(sd)
+        ours.load_state_dict(sd)
+        x1 = torch.randn(2, 9, 32, requires_grad=True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        y1, y2 = theirs(x1), ours(x2)
+        # the reference initialises weights with torch.rand: activations are O(10-100) and the
+        # gradients are differences of large terms, so compare against the tensor's own scale
+        close = lambda a, b: float((a.detach() - b.detach()).abs().max()) <= 5e-5 * float(a.detach().abs().max()) + 1e-6
+        assert close(y1, y2), type(ours).__name__
+        g = torch.randn_like(y1)
+        y1.backward(g)
+        y2.backward(g)
+        assert close(x1.grad, x2.grad)
+        for (k, p), (_, q) in zip(theirs.named_parameters(), ours.named_parameters()):
+            assert close(p.grad, q.grad), k
