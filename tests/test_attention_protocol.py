@@ -554,3 +554,144 @@ def split_epilogue_roles(n_tiles):
 def test_gemm_split_epilogue_protocol(n_tiles):
     for seed in range(40):
         run(split_epilogue_roles(n_tiles), seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM with the ring-buffered epilogue (gemm_sm100_2cta.cuh, kEpiBufs = 6): NB staging buffers
+# indexed by a running sub-tile number q that keeps counting across tiles.  One thread (the issuer)
+# commits one TMA-store group per sub-tile and throttles buffer reuse with
+# cp.async.bulk.wait_group.read; 8 epilogue warps meet at ONE named barrier per sub-tile.
+#   plain : buffer q % NB          - issuer waits "<= NB-2 groups unread" before the closing barrier
+#   aux   : buffer pair q % (NB/2) - two outputs per sub-tile, "<= NB/2-2"
+#   in    : a row-wise input of sub-tile q+P (P = NB/2) is TMA-loaded into buffer (q+P) % NB at the
+#           start of sub-tile q after "<= NB-P-1 groups unread"; the buffer's own mbarrier hands it
+#           to the warps, which overwrite it with the output in place
+# The model runs the store engine (reads buffers out, in commit order, lazily) and the load engine
+# asynchronously and checks that no buffer is overwritten before its store was read out and that
+# every warp reads the input of ITS sub-tile.  `slack` shifts the wait constants: +1 must fail.
+# ------------------------------------------------------------------------------------------------
+def ring_epilogue_roles(mode, subs_per_tile, NB=6, n_warps=4, slack=0, seed=0, store_rate=0.5):
+    rng = random.Random(seed)
+    P = NB // 2
+    n_q = sum(subs_per_tile)
+    groups = []                      # committed store groups: dict(q, bufs, read)
+    buf_store_pending = [None] * NB  # q whose (unread) store still owns the buffer
+    buf_content = [None] * NB        # ("in", q) | ("out", q)
+    in_full = [MBar(1) for _ in range(NB)]
+    loads = []                       # pending input loads (buffer, q)
+    state = {"done": False, "arrived": 0, "generation": 0}
+
+    def unread():
+        return sum(1 for g in groups if not g["read"])
+
+    def store_engine():
+        while True:
+            nxt = next((g for g in groups if not g["read"]), None)
+            if nxt is not None and rng.random() < store_rate:
+                for b in nxt["bufs"]:
+                    assert buf_content[b] == ("out", nxt["q"]), \
+                        f"store of sub-tile {nxt['q']} read buffer {b} holding {buf_content[b]}"
+                    buf_store_pending[b] = None
+                nxt["read"] = True
+                yield True
+            elif nxt is not None:
+                yield True                       # the engine is busy (time passes), not blocked
+            else:
+                yield False
+                if state["done"]:
+                    return
+
+    def load_engine():
+        while True:
+            if loads and rng.random() < 0.5:
+                b, q = loads.pop(0)
+                assert buf_store_pending[b] is None, \
+                    f"input of sub-tile {q} loaded into buffer {b} before store {buf_store_pending[b]} was read"
+                buf_content[b] = ("in", q)
+                in_full[b].arrive()
+                yield True
+            elif loads:
+                yield True
+            else:
+                yield False
+                if state["done"]:
+                    return
+
+    def barrier(my_gen):
+        # bar.sync over the epilogue warps: generation counter
+        state["arrived"] += 1
+        if state["arrived"] == n_warps:
+            state["arrived"] = 0
+            state["generation"] += 1
+        yield True
+        yield from wait(lambda: state["generation"] > my_gen)
+
+    def bufs_of(q):
+        if mode == "aux":
+            pair = 2 * (q % (NB // 2))
+            return [pair, pair + 1]
+        return [q % NB]
+
+    def warp(w):
+        issuer = w == 0
+        pf_q = 0
+        gen = 0
+        in_phase = [0] * NB
+        if issuer and mode == "in":
+            for _ in range(P):
+                if pf_q < n_q:
+                    loads.append((pf_q % NB, pf_q))
+                    pf_q += 1
+        for q in range(n_q):
+            bufs = bufs_of(q)
+            if issuer and mode == "in":
+                yield from wait(lambda: unread() <= NB - P - 1 + slack)
+                if pf_q < n_q:
+                    loads.append((pf_q % NB, pf_q))
+                    pf_q += 1
+            if mode == "in":
+                b = bufs[0]
+                yield from wait(lambda: in_full[b].passed(in_phase[b]))
+                in_phase[b] ^= 1
+                assert buf_content[b] == ("in", q), f"warp {w} sub-tile {q}: buffer holds {buf_content[b]}"
+                yield True
+            for b in bufs:                                   # write the output rows of this warp
+                assert buf_store_pending[b] is None, \
+                    f"warp {w} wrote buffer {b} for sub-tile {q} before store {buf_store_pending[b]} was read"
+            yield True
+            if issuer and mode != "in":
+                limit = (NB // 2 - 2 if mode == "aux" else NB - 2) + slack
+                yield from wait(lambda: unread() <= limit)
+            yield from barrier(gen)
+            gen += 1
+            if issuer:
+                for b in bufs:
+                    buf_content[b] = ("out", q)
+                    buf_store_pending[b] = q
+                groups.append(dict(q=q, bufs=bufs, read=False))
+                yield True
+        if issuer:
+            yield from wait(lambda: unread() == 0)
+            state["done"] = True
+
+    return [warp(w) for w in range(n_warps)] + [store_engine(), load_engine()]
+
+
+@pytest.mark.parametrize("mode", ["plain", "aux", "in"])
+@pytest.mark.parametrize("subs", [[4], [4, 4, 4], [4, 2, 4, 1, 3], [1] * 9])
+def test_gemm_ring_epilogue_protocol(mode, subs):
+    for seed in range(25):
+        run(ring_epilogue_roles(mode, subs, seed=seed, store_rate=(0.5, 0.1, 0.02)[seed % 3]), seed)
+
+
+@pytest.mark.parametrize("mode", ["plain", "aux", "in"])
+def test_gemm_ring_epilogue_wait_constants_are_tight(mode):
+    """One more unread store group than the kernel allows and a buffer is overwritten too early."""
+    failures = 0
+    for seed in range(60):
+        try:
+            # (a slow store engine: the reads lag far enough behind for the window to matter)
+            run(ring_epilogue_roles(mode, [4, 4, 4, 4], slack=1, seed=seed, store_rate=0.02), seed)
+        except AssertionError:
+            failures += 1
+    assert failures > 0
