@@ -94,17 +94,24 @@ def _w_ddp(rank, world, as_view, sync, set_to_none):
         ref_opt.zero_grad()
         (sum(ref(xx).sum() for xx in xs) / world).backward()
         for (n, p), (_, q) in zip(ddp.module.named_parameters(), ref.named_parameters()):
-            assert torch.allclose(p.grad, q.grad, atol=1e-6), (it, n)
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), (as_view, sync, set_to_none, it, n)
         opt.step(); ref_opt.step()
         opt.zero_grad(set_to_none=set_to_none)
         for p, q in zip(ddp.module.parameters(), ref.parameters()):
             assert torch.allclose(p, q, atol=1e-6)
 
 
-@pytest.mark.parametrize("as_view,sync,set_to_none", [(True, False, False), (True, False, True),
-                                                      (False, False, True), (True, True, False)])
-def test_naive_ddp_matches_reference(as_view, sync, set_to_none):
-    run_distributed(_w_ddp, 2, as_view, sync, set_to_none)
+def _w_ddp_all(rank, world):
+    for as_view, sync, set_to_none in [(True, False, False), (True, False, True),
+                                       (False, False, True), (True, True, False)]:
+        _w_ddp(rank, world, as_view, sync, set_to_none)
+        dist.barrier()
+
+
+def test_naive_ddp_matches_reference():
+    """bucket views / copies, overlapped / synchronous reduction, zero_grad with and without
+    set_to_none -- per-rank-distinct data, compared with brute-force averaging every step."""
+    run_distributed(_w_ddp_all, 2, timeout=480.0)
 
 
 class _Branchy(nn.Module):
@@ -275,9 +282,14 @@ def _w_zero(rank, world, bucket_size, overlap):
     assert sd["layout"]["world"] == world
 
 
-@pytest.mark.parametrize("bucket_size,overlap", [(5e8, False), (256, True)])
-def test_zero_optimizer_matches_adam(bucket_size, overlap):
-    run_distributed(_w_zero, 2, bucket_size, overlap)
+def _w_zero_all(rank, world):
+    for bucket_size, overlap in [(5e8, False), (256, True)]:
+        _w_zero(rank, world, bucket_size, overlap)
+        dist.barrier()
+
+
+def test_zero_optimizer_matches_adam():
+    run_distributed(_w_zero_all, 2)
 
 
 def _w_zero_variants(rank, world, variant):
@@ -346,13 +358,27 @@ def _w_zero_variants(rank, world, variant):
     assert n_state < n_total if world > 1 else n_state >= n_total
 
 
-@pytest.mark.parametrize("variant", ["bf16_fp32_master", "bf16_master", "stage1", "no_bucketize",
-                                     "grad_acc", "sgd_momentum", "two_groups"])
-def test_zero_optimizer_variants(variant):
-    run_distributed(_w_zero_variants, 3, variant)
+_ZERO_VARIANTS = ["bf16_fp32_master", "bf16_master", "stage1", "no_bucketize", "grad_acc",
+                  "sgd_momentum", "two_groups"]
+
+
+def _w_zero_variants_all(rank, world):
+    for variant in _ZERO_VARIANTS:
+        _w_zero_variants(rank, world, variant)
+        dist.barrier()
+
+
+def test_zero_optimizer_variants():
+    run_distributed(_w_zero_variants_all, 3, timeout=480.0)
 
 
 # ------------------------------------------------------------------ hybrid ZeRO (node-local shards)
+def _w_hybrid_zero_all(rank, world):
+    for mode, as_view, overlap in _HYBRID_VARIANTS:
+        _w_hybrid_zero(rank, world, mode, as_view, overlap)
+        dist.barrier()
+
+
 def _w_hybrid_zero(rank, world, mode, as_view, overlap):
     """4 ranks = 2 "nodes" x 2: ZeRO shards inside the node, the cross-node average comes from
     NaiveDDP (either construction order, world or inter-node group) or from ``outer_group``.
@@ -397,11 +423,15 @@ def _w_hybrid_zero(rank, world, mode, as_view, overlap):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (mode, it, (p - q).abs().max())
 
 
-@pytest.mark.parametrize("mode,as_view,overlap", [
-    ("ddp_world_first", True, True), ("ddp_world_first", False, False),
-    ("ddp_inter_first", True, True), ("zero_first", True, True), ("outer_group", True, True)])
-def test_hybrid_zero_matches_adam(mode, as_view, overlap):
-    run_distributed(_w_hybrid_zero, 4, mode, as_view, overlap)
+_HYBRID_VARIANTS = [("ddp_world_first", True, True), ("ddp_world_first", False, False),
+                    ("ddp_inter_first", True, True), ("zero_first", True, True),
+                    ("outer_group", True, True)]
+
+
+def test_hybrid_zero_matches_adam():
+    """Five compositions, one after the other in the same four processes (a fresh model, fresh
+    engines and fresh groups each; the assertion message names the composition)."""
+    run_distributed(_w_hybrid_zero_all, 4, timeout=480.0)
 
 
 # ------------------------------------------------------------------ sharded EMA
@@ -665,9 +695,14 @@ def _w_tp_block(rank, world, sequence_parallel):
     assert torch.allclose(par.mlp.fc2.linear.bias.grad, serial.mlp.fc2.bias.grad, atol=1e-4)
 
 
-@pytest.mark.parametrize("sp", [False, True])
-def test_tp_block_matches_serial(sp):
-    run_distributed(_w_tp_block, 2, sp)
+def _w_tp_block_both(rank, world):
+    for sp in (False, True):
+        _w_tp_block(rank, world, sp)
+        dist.barrier()
+
+
+def test_tp_block_matches_serial():
+    run_distributed(_w_tp_block_both, 2)
 
 
 def _w_tp_transformer(rank, world):

@@ -45,19 +45,44 @@ def _env():
     return env
 
 
+@pytest.fixture(scope="module")
+def launched():
+    """All example scripts are started together (each is its own torchrun job on its own port) and
+    collected once: the wall time of this file is the slowest example, not their sum."""
+    jobs = []
+    for script, ranks, _ in DISTRIBUTED:
+        jobs.append((script, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                              f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
+                              "--master-port", str(_free_port()),
+                              os.path.join(ROOT, "examples", script), "--cpu"]))
+    for script, _ in SINGLE:
+        jobs.append((script, [sys.executable, os.path.join(ROOT, "examples", script)]))
+    out = {}
+    width = 5                                   # jobs in flight (each is 1-4 processes)
+    for i in range(0, len(jobs), width):
+        procs = {script: subprocess.Popen(cmd, cwd=ROOT, env=_env(), stdout=subprocess.PIPE,
+                                          stderr=subprocess.PIPE, text=True)
+                 for script, cmd in jobs[i:i + width]}
+        for script, p in procs.items():
+            try:
+                so, se = p.communicate(timeout=600)
+                out[script] = (p.returncode, so, se)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                so, se = p.communicate()
+                out[script] = (-9, so, se + "\n[timeout]")
+    return out
+
+
 @pytest.mark.parametrize("script,ranks,expect", DISTRIBUTED, ids=[d[0] for d in DISTRIBUTED])
-def test_distributed_example_runs_on_gloo(script, ranks, expect):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "examples", script), "--cpu"]
-    r = subprocess.run(cmd, cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-2500:])
-    assert expect in r.stdout, r.stdout[-1500:]
+def test_distributed_example_runs_on_gloo(launched, script, ranks, expect):
+    rc, so, se = launched[script]
+    assert rc == 0, (so[-1500:], se[-2500:])
+    assert expect in so, so[-1500:]
 
 
 @pytest.mark.parametrize("script,expect", SINGLE, ids=[d[0] for d in SINGLE])
-def test_single_process_example_runs_on_cpu(script, expect):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script)], cwd=ROOT, env=_env(),
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-2500:])
-    assert expect in r.stdout, r.stdout[-1500:]
+def test_single_process_example_runs_on_cpu(launched, script, expect):
+    rc, so, se = launched[script]
+    assert rc == 0, (so[-1500:], se[-2500:])
+    assert expect in so, so[-1500:]
