@@ -1375,3 +1375,164 @@ def _w_clip_variants(rank, world):
 
 def test_clip_grad_norm_variants_and_attention_weight_slicing():
     run_distributed(_w_clip_variants, 4)
+
+
+# ------------------------------------------------------------------ fused SP autograd wiring (CPU twin)
+def _w_tp_fused_twin(rank, world):
+    """parallel/tensor_parallel/tp_fused.py: the autograd functions around the fused GEMM+collective
+    kernels -- which tensors are saved, which product pairs with which collective in backward, the
+    GELU derivative riding on the all-gather GEMM -- run here with the three kernel entry points
+    replaced by their definitions in torch + gloo (all_gather -> matmul, matmul -> reduce_scatter,
+    matmul -> all_reduce).  Outputs and ALL gradients must match plain autograd over the unfused
+    formulation (what the reference computes: tp_utils.py:52-159, mlp.py:69-78)."""
+    import torch.nn.functional as F
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.ops import linear as L
+    from torchdistpackage_b200.parallel.tensor_parallel import tp_fused as tf
+
+    def ag(x):                                              # all-gather along dim 0
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x.contiguous())
+        return torch.cat(parts, 0)
+
+    def rs(y):                                              # reduce-scatter along dim 0 (sum)
+        y = y.clone()
+        dist.all_reduce(y)
+        return y.chunk(world, 0)[rank].contiguous()
+
+    def act_apply(z, code):
+        if code == L.ACT_NONE:
+            return z
+        return F.gelu(z, approximate="tanh" if code == L.ACT_GELU_TANH else "none")
+
+    def dact(z, code):
+        zf = z.detach().clone().requires_grad_(True)
+        base = L.ACT_GELU_TANH if code == L.ACT_DGELU_TANH else L.ACT_GELU_ERF
+        with torch.enable_grad():
+            a = act_apply(zf, base)
+        return torch.autograd.grad(a, zf, torch.ones_like(a))[0]
+
+    class Token:                                            # what _gathered_or_regather inspects
+        pass
+
+    def fake_ag_gemm(ctx, name, x_shard, w, trans_b, bias=None, act=0, aux_in=None, want_aux_out=False):
+        full = ag(x_shard)
+        z = full @ (w.t() if trans_b else w)
+        if bias is not None:
+            z = z + bias
+        if act in (L.ACT_DGELU_TANH, L.ACT_DGELU_ERF):
+            out = z * dact(aux_in, act)
+        else:
+            out = act_apply(z, act)
+        full._tdp_token = Token()
+        return out, full, (z if want_aux_out else None)
+
+    def fake_gemm_rs(ctx, name, a, w, trans_b, bias=None, residual=None):
+        y = rs(a @ (w.t() if trans_b else w))
+        if bias is not None:
+            y = y + bias
+        return y if residual is None else y + residual
+
+    def fake_gemm_ar(ctx, name, a, w, trans_b, bias=None):
+        y = a @ (w.t() if trans_b else w)
+        dist.all_reduce(y)
+        return y if bias is None else y + bias
+
+    saved = (tf._ag_gemm, tf._gemm_rs, tf._gemm_ar, tf._gathered_or_regather)
+    saved_l = (L.gemm, L.colsum)
+    tf._ag_gemm, tf._gemm_rs, tf._gemm_ar = fake_ag_gemm, fake_gemm_rs, fake_gemm_ar
+    tf._gathered_or_regather = lambda fctx, gathered, token, shard: gathered
+    # the plain GEMM / column-sum entry points of the native extension, by definition
+    L.gemm = lambda a, b, trans_a=False, trans_b=False, **kw: \
+        (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+    L.colsum = lambda x, out_dtype=None: x.sum(0)
+    try:
+        torch.manual_seed(5)                               # same weights everywhere ...
+        T, K, Hh = 8, 6, 10
+        w1, b1 = torch.randn(K, Hh), torch.randn(Hh)
+        w2, b2 = torch.randn(Hh, K), torch.randn(K)
+        # ... tensor-parallel shards of them on this rank
+        w1s, b1s = w1.chunk(world, 1)[rank].contiguous(), b1.chunk(world)[rank].contiguous()
+        w2s = w2.chunk(world, 0)[rank].contiguous()
+        torch.manual_seed(100 + rank)
+        x_shard = torch.randn(T // world, K)                # sequence shard of the activations
+        g_shard = torch.randn(T // world, K)                # incoming gradient (shard)
+
+        def leaves(*ts):
+            return [t.detach().clone().requires_grad_(True) for t in ts]
+
+        def grads_of(y, g, params):
+            return torch.autograd.grad(y, params, g, allow_unused=True)
+
+        # (1) sp_mlp  ==  RS(gelu(AG(x) @ W1 + b1) @ W2) + b2
+        pa = leaves(x_shard, w1s, b1s, w2s, b2)
+        ya = tf.sp_mlp(None, pa[0], pa[1], pa[2], pa[3], pa[4], act="gelu_tanh")
+        pb = leaves(x_shard, w1s, b1s, w2s, b2)
+
+        class AG(torch.autograd.Function):                  # reference formulation with its own
+            @staticmethod                                   # collectives' autograd rules
+            def forward(ctx, t):
+                return ag(t)
+
+            @staticmethod
+            def backward(ctx, gfull):
+                return rs(gfull)
+
+        class RS(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, t):
+                return rs(t)
+
+            @staticmethod
+            def backward(ctx, gsh):
+                return ag(gsh)
+
+        yb = RS.apply(F.gelu(AG.apply(pb[0]) @ pb[1] + pb[2], approximate="tanh") @ pb[3]) + pb[4]
+        assert torch.allclose(ya, yb, atol=1e-5)
+        for name, ga, gb in zip(("dx", "dw1", "db1", "dw2", "db2"), grads_of(ya, g_shard, pa),
+                                grads_of(yb, g_shard, pb)):
+            assert torch.allclose(ga, gb, atol=1e-4), name
+
+        # (2) ag_linear / linear_rs as separate ops
+        pa, pb = leaves(x_shard, w1s, b1s), leaves(x_shard, w1s, b1s)
+        ya = tf.ag_linear(None, pa[0], pa[1], pa[2])
+        yb = AG.apply(pb[0]) @ pb[1] + pb[2]
+        gfull = torch.randn_like(yb)
+        assert torch.allclose(ya, yb, atol=1e-5)
+        for name, ga, gb in zip(("dx", "dw", "db"), grads_of(ya, gfull, pa), grads_of(yb, gfull, pb)):
+            assert torch.allclose(ga, gb, atol=1e-4), name
+        a_full = torch.randn(T, Hh // world)
+        pa, pb = leaves(a_full, w2s, b2), leaves(a_full, w2s, b2)
+        ya = tf.linear_rs(None, pa[0], pa[1], pa[2])
+        yb = RS.apply(pb[0] @ pb[1]) + pb[2]
+        assert torch.allclose(ya, yb, atol=1e-5)
+        for name, ga, gb in zip(("da", "dw", "db"), grads_of(ya, g_shard, pa), grads_of(yb, g_shard, pb)):
+            assert torch.allclose(ga, gb, atol=1e-4), name
+
+        # (3) linear_ar (row-parallel without SP): y = all_reduce(a @ W) + b, identity in backward
+        pa, pb = leaves(a_full, w2s, b2), leaves(a_full, w2s, b2)
+        ya = tf.linear_ar(None, pa[0], pa[1], pa[2])
+
+        class AR(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, t):
+                t = t.clone()
+                dist.all_reduce(t)
+                return t
+
+            @staticmethod
+            def backward(ctx, g_):
+                return g_
+        yb = AR.apply(pb[0] @ pb[1]) + pb[2]
+        gy = torch.randn(T, K)
+        assert torch.allclose(ya, yb, atol=1e-5)
+        for name, ga, gb in zip(("da", "dw", "db"), grads_of(ya, gy, pa), grads_of(yb, gy, pb)):
+            assert torch.allclose(ga, gb, atol=1e-4), name
+    finally:
+        tf._ag_gemm, tf._gemm_rs, tf._gemm_ar, tf._gathered_or_regather = saved
+        L.gemm, L.colsum = saved_l
+    del tdp
+
+
+def test_fused_sequence_parallel_autograd_wiring_cpu_twin():
+    run_distributed(_w_tp_fused_twin, 2)
