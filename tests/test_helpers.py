@@ -551,3 +551,57 @@ def test_gpt2_and_moe_models_train_on_cpu():
             experts = model.expert_parameters()
             assert experts and set(model.ddp_ignore_names()) == set(experts)
             assert all(".moe." in n for n in experts), sorted(experts)[:3]
+
+
+def test_remaining_small_helpers():
+    from torchdistpackage_b200.utils.flat import flatten_like, align_up
+    from torchdistpackage_b200.ops._loader import have_native, use_native_for
+    from torchdistpackage_b200.tools.module_profiler import output_same_as_input
+    from torchdistpackage_b200.tools.debug_nan import register_nan_hooks
+    from torchdistpackage_b200.parallel import NativeScalerPP
+    from torchdistpackage_b200.dist.py_comm_test import CommResult
+    from torchdistpackage_b200.tools.int8_linear import Int8WeightOnlyLinear
+
+    ts = [torch.arange(5.0), torch.ones(2, 3)]
+    flat, views = flatten_like(ts, align_elems=8)
+    assert flat.numel() == 16 and align_up(5, 8) == 8
+    assert torch.equal(views[0], ts[0]) and views[1].data_ptr() == flat[8:].data_ptr()
+    views[1].zero_()
+    assert float(flat[8:14].abs().sum()) == 0.0                    # views alias the flat buffer
+    buf = torch.zeros(32)
+    assert flatten_like(ts, out=buf)[0] is buf
+
+    assert isinstance(have_native(), bool) and use_native_for(torch.zeros(1)) is False
+
+    x = torch.ones(2)
+    assert output_same_as_input(x, x) and output_same_as_input(x, (x,))
+    assert not output_same_as_input(x, (x, x)) and not output_same_as_input([x], x)
+
+    # the backward hook fires on gradients: a NaN produced only in backward is located too
+    class BadGrad(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t * 1.0
+
+        @staticmethod
+        def backward(ctx, g):
+            return g * float("nan")
+
+    class Wrap(nn.Module):
+        def forward(self, t):
+            return BadGrad.apply(t)
+    m = nn.Sequential(nn.Linear(3, 3), Wrap())
+    register_nan_hooks(m)
+    with pytest.raises(FloatingPointError):
+        m(torch.randn(2, 3, requires_grad=True)).sum().backward()
+
+    sc = NativeScalerPP(enabled=True, init_scale=8.0)
+    assert float(sc.scale(torch.tensor(2.0))) == 16.0
+    sd = sc.state_dict()
+    sc2 = NativeScalerPP(enabled=True)
+    sc2.load_state_dict(sd)
+    assert sc2.state_dict()["scale"] == 8.0
+
+    r = CommResult(dict(busbw_gbs=1.23456, ms=2.0, mode="all_reduce"))
+    assert tuple(r) == (1.235, 0.002) and set(r.keys()) == {"busbw_gbs", "ms", "mode"} and r["mode"] == "all_reduce"
+    assert "int8" in repr(Int8WeightOnlyLinear.from_linear(nn.Linear(4, 4)))
