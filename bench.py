@@ -53,6 +53,10 @@ def parse_args():
                          "outside the timed region; auto = only at --gpus 8")
     ap.add_argument("--no-checks", action="store_true",
                     help="skip the untimed gradient check / exposed-communication measurement")
+    ap.add_argument("--config", default="dp", choices=["dp", "tp", "moe", "mixed"],
+                    help="dp = the headline (BASELINE config #2, this file); tp / moe / mixed = "
+                         "BASELINE configs #3 / #4 / #5, handed to scripts/bench_{tp,moe,mixed}.py "
+                         "with the same --impl / --steps / --warmup (one JSON line each)")
     return ap.parse_args()
 
 
@@ -446,6 +450,10 @@ def emit_json(obj) -> None:
 
 def main():
     args = parse_args()
+    if args.config != "dp":
+        script = dict((name, path) for name, path, _ in OTHER_CONFIGS)[args.config]
+        os.execv(sys.executable, [sys.executable, os.path.join(ROOT, script), "--impl", args.impl,
+                                  "--steps", str(args.steps), "--warmup", str(args.warmup)])
     _quiet_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
