@@ -1536,3 +1536,85 @@ def _w_tp_fused_twin(rank, world):
 
 def test_fused_sequence_parallel_autograd_wiring_cpu_twin():
     run_distributed(_w_tp_fused_twin, 2)
+
+
+# ------------------------------------------------------------------ differential: TP block vs the reference on gloo
+def _w_tp_block_vs_reference(rank, world):
+    """The unmodified reference's ParallelBlock (non-SP: its collectives are plain all_reduce, which
+    gloo has) and this package's, both initialised from the same serial block with
+    ``init_from_full``: same forward, same weight gradients.  (Input gradients are NOT compared:
+    the reference's column-parallel layers do not all-reduce them, SURVEY.md 2.6 #11 -- ours must
+    match the serial block instead, which test_tp_block_matches_serial checks.)"""
+    import os
+    import sys
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    sys.path.insert(0, ref_dir)
+    try:
+        from torchdistpackage.parallel.tensor_parallel.transformer import Block as RBlock, \
+            ParallelBlock as RParallelBlock
+    finally:
+        sys.path.remove(ref_dir)
+    import torchdistpackage_b200 as tdp
+    from torchdistpackage_b200.parallel import Block, ParallelBlock
+    tdp.fix_rand(0)
+    dim, heads = 32, 4
+    serial_ref = RBlock(dim, num_heads=heads)
+    with torch.no_grad():
+        for p in serial_ref.parameters():              # torch.rand weights blow activations up
+            p.mul_(0.1)
+    serial = Block(dim, num_heads=heads)
+    serial.load_state_dict(serial_ref.state_dict())    # same names and shapes
+    theirs = RParallelBlock(dim, num_heads=heads, sequence_parallel=False)
+    ours = ParallelBlock(dim, num_heads=heads, sequence_parallel=False)
+    theirs.init_from_full(serial_ref)
+    ours.init_from_full(serial)
+    assert [(n, tuple(p.shape)) for n, p in theirs.named_parameters()] == \
+           [(n, tuple(p.shape)) for n, p in ours.named_parameters()]
+    for (n, p), (_, q) in zip(theirs.named_parameters(), ours.named_parameters()):
+        if n.endswith("bias") and not n.startswith("ln"):
+            continue        # the reference leaves row-parallel / qkv biases at zero (init_from_full
+                            # copies weights only); ours copies them from the serial block
+        assert torch.equal(p, q), n
+    with torch.no_grad():   # align the biases: zero everywhere, as in the reference after init
+        for blk in (theirs, ours):
+            for n, p in blk.named_parameters():
+                if n.endswith("bias") and not n.startswith("ln"):
+                    p.zero_()
+    torch.manual_seed(3)
+    x = torch.randn(2, 6, dim)
+    y_t = theirs(x.clone())
+    y_o = ours(x.clone())
+    scale = float(y_t.detach().abs().max())
+    assert float((y_t - y_o).detach().abs().max()) <= 2e-5 * scale + 1e-6
+    g = torch.randn_like(y_t)
+    y_t.backward(g)
+    y_o.backward(g)
+    checked = 0
+    for (n, p), (_, q) in zip(theirs.named_parameters(), ours.named_parameters()):
+        # Only the MLP weights see the same upstream gradient in both implementations: everything
+        # before the MLP receives, in the reference, the *partial* input gradient of the
+        # column-parallel fc1 (no all-reduce in its backward, defect #11), so its attention / LN
+        # gradients are not what the serial block gives -- ours are (test_tp_block_matches_serial).
+        if not (n.startswith("mlp.") and n.endswith("weight")):
+            continue
+        s_ = float(p.grad.abs().max())
+        assert float((p.grad - q.grad).abs().max()) <= 5e-5 * s_ + 1e-6, n
+        checked += 1
+    assert checked == 2
+    # and the reference's attention-side gradients really are different from the serial truth
+    xs = x.clone().requires_grad_(True)
+    ys = serial(xs)
+    ys.backward(g)
+    tp = rank
+    full = serial.attn.proj.weight.grad                      # [dim, dim]; row-parallel shard = rows
+    mine = full[tp * (dim // world):(tp + 1) * (dim // world)]
+    ours_g = dict(ours.named_parameters())["attn.proj.linear.weight"].grad
+    assert float((ours_g - mine).abs().max()) <= 5e-5 * float(mine.abs().max()) + 1e-6
+
+
+def test_parallel_block_matches_the_reference_on_gloo():
+    import os
+    if not os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                      "baseline", "_ref", "torchdistpackage")):
+        pytest.skip("reference arm not installed (baseline/_ref)")
+    run_distributed(_w_tp_block_vs_reference, 2)
