@@ -139,3 +139,55 @@ def test_moe_slot_plan_is_a_partial_injection(tokens, k, n_exp, cap, data):
                                     torch.div(p.dst_row.clamp_min(0), ep * cap, rounding_mode="floor"),
                                     weights=p.keep.float(), minlength=n_exp)
         assert float(per_expert.max()) <= cap
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 40), st.integers(1, 40), st.booleans()), min_size=1, max_size=10),
+       st.sampled_from([2e-4, 1e-3, 5e-3, 25.0]), st.booleans())
+def test_ddp_bucket_plan_invariants(layers, cap_mb, as_view):
+    """Whatever the parameter shapes and the bucket size: every trainable parameter lives in exactly
+    one bucket, slots are 512-byte aligned and disjoint, only an oversized parameter may exceed
+    the cap (alone), buckets fill in reverse registration order, gradients written through
+    ``p.grad`` land in the flat buffer."""
+    import torch.nn as nn
+    import torchdistpackage_b200 as tdp
+    mods = []
+    for fin, fout, bias in layers:
+        mods.append(nn.Linear(fin, fout, bias=bias))
+    model = nn.Sequential(*mods)
+    ddp = tdp.NaiveDDP(model, gradient_as_bucket_view=as_view, bucket_cap_mb=cap_mb)
+    try:
+        red = ddp.reducer
+        names = [n for n, p in model.named_parameters()]
+        placed = [n for b in red.buckets for n in b.names]
+        assert sorted(placed) == sorted(names)
+        cap_bytes = int(cap_mb * 1024 * 1024)
+        for b in red.buckets:
+            spans = []
+            for n in b.names:
+                v = b.views[n]
+                off = (v.data_ptr() - b.buffer.data_ptr())
+                assert off % 512 == 0 and v.numel() == dict(model.named_parameters())[n].numel()
+                spans.append((off, off + v.numel() * v.element_size()))
+            spans.sort()
+            assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+            assert spans[-1][1] <= b.buffer.numel() * b.buffer.element_size()
+            if len(b.names) > 1:
+                assert spans[-1][1] <= max(cap_bytes, 512 * len(b.names))
+        # reverse registration order: the last layer's parameters are in the first bucket
+        assert names[-1] in red.buckets[0].names
+        x = torch.randn(3, layers[0][0])
+        y = x
+        for (fin, fout, _), m in zip(layers, mods):
+            if y.shape[-1] != fin:
+                y = torch.randn(3, fin)
+            y = m(y)
+        y.sum().backward()
+        ddp.reduce_gradients()
+        if as_view:
+            for n, p in model.named_parameters():
+                if p.grad is not None:
+                    b = red.param_bucket[n]
+                    assert p.grad.data_ptr() == b.views[n].data_ptr()
+    finally:
+        ddp.remove_hooks()
