@@ -605,3 +605,39 @@ def test_remaining_small_helpers():
     r = CommResult(dict(busbw_gbs=1.23456, ms=2.0, mode="all_reduce"))
     assert tuple(r) == (1.235, 0.002) and set(r.keys()) == {"busbw_gbs", "ms", "mode"} and r["mode"] == "all_reduce"
     assert "int8" in repr(Int8WeightOnlyLinear.from_linear(nn.Linear(4, 4)))
+
+
+def test_engines_work_without_a_process_group():
+    """Single-process debugging: every engine degrades to its serial meaning when
+    torch.distributed was never initialised (the reference needs a process group -- and CUDA --
+    for all of them)."""
+    import copy
+    import torch.distributed as dist
+    from torchdistpackage_b200.parallel import clip_grad_norm_
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    tdp.tpc.reset()
+    torch.manual_seed(0)
+    m = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 4))
+    r = copy.deepcopy(m)
+    ddp = tdp.NaiveDDP(m, gradient_as_bucket_view=True)
+    z = tdp.Bf16ZeroOptimizer(torch.optim.AdamW(m.parameters(), lr=1e-2), overlap_comm=True)
+    o = torch.optim.AdamW(r.parameters(), lr=1e-2)
+    ema = tdp.ShardedEMA(m)
+    for _ in range(3):
+        x = torch.randn(5, 8)
+        z.zero_grad()
+        ddp(x).sum().backward()
+        ddp.reduce_gradients()
+        norm = clip_grad_norm_(list(m.parameters()), 1e9, zero_optimizer=z)
+        z.step()
+        o.zero_grad()
+        r(x).sum().backward()
+        want = torch.sqrt(sum(q.grad.pow(2).sum() for q in r.parameters()))
+        o.step()
+        assert torch.allclose(norm, want, rtol=1e-5)
+        ema.update(m, decay=0.5)
+    for p, q in zip(m.parameters(), r.parameters()):
+        assert torch.allclose(p, q, atol=1e-6)
+    assert len(ema.state_dict_cpu()) == 4
+    ddp.remove_hooks()
