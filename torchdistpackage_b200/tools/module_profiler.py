@@ -228,15 +228,21 @@ def get_model_profile(model: nn.Module, args: tuple = (), kwargs: Optional[dict]
     the report (reference: :144-171, same defaults).  ``backward=True`` also runs
     ``output.sum().backward()`` so the report carries backward times."""
     kwargs = kwargs or {}
-    with torch.set_grad_enabled(backward):
-        model(*args, **kwargs)                               # warm-up (allocator, autotuning)
-    recs = register_profile_hooks(model, max_depth=None, backward=backward)
-    try:
+
+    def run():
         with torch.set_grad_enabled(backward):
             out = model(*args, **kwargs)
             if backward:
                 loss = out if isinstance(out, torch.Tensor) else out[0]
                 loss.float().sum().backward()
+
+    run()                          # warm-up, backward included (allocator, library heuristics:
+    #                                the first backward GEMM of a shape costs milliseconds)
+    if backward:
+        model.zero_grad(set_to_none=True)
+    recs = register_profile_hooks(model, max_depth=None, backward=backward)
+    try:
+        run()
     finally:
         recs.remove()
     return report_prof(recs, sort=sort, topn=topn, max_depth=max_depth, min_mem=min_mem)
