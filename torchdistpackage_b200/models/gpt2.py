@@ -24,7 +24,6 @@ from typing import Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ..ops import fused as F_ops
 from ..ops import linear as L_ops

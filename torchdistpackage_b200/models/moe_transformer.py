@@ -13,7 +13,6 @@ from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ..moe.layer import MoELayer
 from ..ops import fused as F_ops

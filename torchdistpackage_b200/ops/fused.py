@@ -8,7 +8,7 @@ PyTorch fallbacks for CPU tensors.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.nn.functional as F

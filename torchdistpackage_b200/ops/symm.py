@@ -12,7 +12,7 @@ Signal pad word layout (uint32 words, see collectives.cu):
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist

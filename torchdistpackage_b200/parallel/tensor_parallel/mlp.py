@@ -10,7 +10,6 @@ GEMM and the reduce-scatter into the fc2 GEMM (tp_fused.py).
 """
 from __future__ import annotations
 
-import torch
 from torch import nn as nn
 
 from ...ops import linear as _ops_linear

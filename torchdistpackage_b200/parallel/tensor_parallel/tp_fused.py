@@ -29,7 +29,7 @@ from __future__ import annotations
 
 import os
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 import torch.distributed as dist
