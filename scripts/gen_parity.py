@@ -176,7 +176,8 @@ side by side.  Paths are relative to `torchdistpackage_b200/` unless they start 
 `scripts/`, `examples/`, `docs/` or `profiles/`.  "Test" is what pins the behaviour on every run (`pytest -m "not gpu"` on gloo,
 `pytest -m gpu` on a B200); "Measured" points into `profiles/SUMMARY.md`.  Names, import paths and
 call signatures of the reference are pinned by `tests/test_api_surface.py`
-(`import torchdistpackage_b200 as torchdistpackage` is the switch); the device-free parts of the
+(`import torchdistpackage_b200 as torchdistpackage` is the switch, or `compat.install_alias()`
+to keep a script's `from torchdistpackage.x.y import z` lines untouched); the device-free parts of the
 reference (rank layouts for 76 world-size / axis-order combinations, MoE group splits, partition
 and flatten helpers, bucket alignment, profiler and NaN-helper conventions) are run side by side
 with this package in `tests/test_differential_vs_reference.py`, importing the unmodified

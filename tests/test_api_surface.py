@@ -306,3 +306,62 @@ def test_parity_document_points_at_real_code():
         assert os.path.exists(full), path
         with open(full) as f:
             assert int(line) <= sum(1 for _ in f), (path, line)
+
+
+def test_import_alias_runs_reference_style_code_unmodified(tmp_path):
+    """``compat.install_alias()``: a script written against the reference -- its Readme example and
+    the deep module paths its examples import -- runs with only the alias line added, and gets the
+    same module objects as ``torchdistpackage_b200`` (one ``tpc``).  In a subprocess: the alias is
+    process-wide by design."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "user_script.py"
+    script.write_text('''
+import sys
+sys.path.insert(0, %r)
+import torchdistpackage_b200.compat as compat
+assert compat.install_alias()
+
+# ---- from here on: code as written for the reference (Readme.md:21-45, examples/*) ----
+import torch
+import torch.distributed as dist
+from torchdistpackage import setup_distributed, test_comm, tpc
+from torchdistpackage import NaiveDDP, Bf16ZeroOptimizer, ShardedEMA, fix_rand
+from torchdistpackage.dist.launch_from_slurm import setup_distributed as sd
+from torchdistpackage.parallel.pipeline_parallel.pipeline_sched import forward_backward
+from torchdistpackage.parallel.pipeline_parallel import comm, clip_grad_parallel, pipeline_helper
+from torchdistpackage.parallel.tensor_parallel.transformer import Transformer
+from torchdistpackage.parallel import Block, TpMlp
+from torchdistpackage.tools.module_profiler import get_model_profile
+from torchdistpackage.ddp.naive_ddp import create_moe_dp_hooks, moe_dp_iter_step
+
+setup_distributed("gloo")
+world_size, pp_size = dist.get_world_size(), 1
+dist_config = [("data", world_size / (1 * pp_size)), ("pipe", pp_size), ("tensor", 1)]
+tpc.setup_process_groups(dist_config)
+tmp = torch.rand([100, 1024])
+dist.broadcast(tmp, tpc.get_ranks_in_group("model")[0], tpc.get_group("model"))
+assert test_comm()
+model = NaiveDDP(torch.nn.Linear(4, 4), sync=False, gradient_as_bucket_view=True)
+model(torch.randn(2, 4)).sum().backward()
+model.reduce_gradients()
+
+import torchdistpackage, torchdistpackage_b200
+import torchdistpackage.dist.process_topo as a
+import torchdistpackage_b200.dist.process_topo as b
+assert torchdistpackage is torchdistpackage_b200 and a is b and a.tpc is tpc and sd is setup_distributed
+print("REFERENCE_STYLE_SCRIPT_OK")
+''' % root)
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith(("SLURM_", "TORCHELASTIC")) and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK",
+                                                                         "MASTER_ADDR", "MASTER_PORT")}
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "REFERENCE_STYLE_SCRIPT_OK" in r.stdout, (r.stdout[-800:], r.stderr[-2000:])
+    # an already imported foreign package of that name is left alone
+    code = ("import sys, types; sys.path.insert(0, %r); sys.modules['torchdistpackage'] = types.ModuleType('torchdistpackage');"
+            "import torchdistpackage_b200.compat as c; assert c.install_alias() is False; "
+            "assert c.install_alias(force=True) is True; import torchdistpackage, torchdistpackage_b200; "
+            "assert torchdistpackage is torchdistpackage_b200; print('OK')" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-1500:]
