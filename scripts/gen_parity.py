@@ -212,7 +212,12 @@ SASS listings per kernel family: `profiles/sass/`; ncu summaries: `profiles/ncu/
 ## 2.5 Examples, explorations, docs
 
 Every script below runs to its "OK" line on CPU / gloo under torchrun in `tests/test_examples_cpu.py`
-(the reference's examples are its only tests; here they are exercised on every test run).
+(the reference's examples are its only tests; here they are exercised on every test run).  In
+addition the reference's OWN scripts E01-E06 and E08 run **unmodified** against this package
+(`tests/test_reference_examples.py`: import alias + `.cuda()` as identity on a CPU host) and pass
+their own assertions -- NaiveDDP and ZeRO vs torch DDP on an MLP and resnet50, ShardedEMA bit-exact
+on resnet50, 1F1B with pipe=2 x data=2, TpMlp / TpAttention forward and weight gradients;
+record: `profiles/r2/reference_examples_unmodified_on_gloo.txt`.
 
 {table(["ID", "Here"], rows_extra)}
 
