@@ -53,10 +53,11 @@ def parse_args():
                          "outside the timed region; auto = only at --gpus 8")
     ap.add_argument("--no-checks", action="store_true",
                     help="skip the untimed gradient check / exposed-communication measurement")
-    ap.add_argument("--config", default="dp", choices=["dp", "tp", "moe", "mixed"],
+    ap.add_argument("--config", default="dp", choices=["dp", "tp", "moe", "mixed", "cpu"],
                     help="dp = the headline (BASELINE config #2, this file); tp / moe / mixed = "
                          "BASELINE configs #3 / #4 / #5, handed to scripts/bench_{tp,moe,mixed}.py "
-                         "with the same --impl / --steps / --warmup (one JSON line each)")
+                         "with the same --impl / --steps / --warmup (one JSON line each); cpu = "
+                         "config #1, the CPU / gloo plumbing check (scripts/bench_cpu_mlp.py)")
     return ap.parse_args()
 
 
@@ -451,7 +452,8 @@ def emit_json(obj) -> None:
 def main():
     args = parse_args()
     if args.config != "dp":
-        script = dict((name, path) for name, path, _ in OTHER_CONFIGS)[args.config]
+        script = dict([(name, path) for name, path, _ in OTHER_CONFIGS] +
+                      [("cpu", "scripts/bench_cpu_mlp.py")])[args.config]
         os.execv(sys.executable, [sys.executable, os.path.join(ROOT, script), "--impl", args.impl,
                                   "--steps", str(args.steps), "--warmup", str(args.warmup)])
     _quiet_stdout()

@@ -86,3 +86,22 @@ def test_single_process_example_runs_on_cpu(launched, script, expect):
     rc, so, se = launched[script]
     assert rc == 0, (so[-1500:], se[-2500:])
     assert expect in so, so[-1500:]
+
+
+def test_baseline_config_1_cpu_gloo_bench_line():
+    """BASELINE config #1 (NaiveDDP on the reference's 2-layer MLP, world 2, CPU / gloo) through
+    ``bench.py --config cpu``: one JSON line with a throughput and an exact gradient check."""
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "bench.py"), "--config", "cpu", "--steps", "50", "--warmup", "5"]
+    r = subprocess.run(cmd, cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-500:]
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "ours" and rec["n_procs"] == 2 and rec["value"] > 0
+    assert rec["grad_check_max_abs"] < 1e-6
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "cpu", "--impl", "reference"],
+                       cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "unavailable" in json.loads(r.stdout.strip().splitlines()[-1])
